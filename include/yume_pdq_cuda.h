@@ -1,0 +1,218 @@
+/*
+ * yume_pdq_cuda.h -- C ABI of the B200-native (sm_100a) PDQ hash-and-match engine.
+ *
+ * Drop-in boundary for the hot path of eternal-flame-AD/yume-pdq.  Two groups
+ * of entry points:
+ *
+ *  (A) the reference's own C ABI, same names / signatures / semantics
+ *      (/root/reference include/yume_pdq.h:22-150, src/lib.rs:136-284), now
+ *      executed on the GPU;
+ *  (B) batched `yume_pdq_cuda_*` entry points that the Rust side
+ *      (`impl Kernel for CudaKernel`, `impl PDQMatcher for CudaMatcher`,
+ *      integration/rust/) and the Python/C++ hosts bind.  Per-frame trait calls
+ *      cannot feed a GPU, so every stage of the `Kernel` trait
+ *      (src/kernel/mod.rs:268-497) is exported in batched form.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Every function in
+ * (B) returns an int: 0 = OK, > 0 = a cudaError_t value, < 0 = YUME_PDQ_CUDA_E_*.
+ * Unless stated otherwise a data pointer may be a HOST pointer (pageable or
+ * pinned) or a DEVICE pointer on `device`; the library detects which.  When all
+ * data pointers are device pointers the call is asynchronous on `stream`
+ * (a cudaStream_t passed as void*, NULL = default stream); with any host
+ * pointer the call stages through the device and returns after completion.
+ * There is no CPU fallback: without a usable CUDA device every call fails with
+ * YUME_PDQ_CUDA_E_NO_DEVICE.
+ */
+#ifndef YUME_PDQ_CUDA_H
+#define YUME_PDQ_CUDA_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ (A) --
+ * Reference ABI, include/yume_pdq.h:22-25 / build.rs:389-429 */
+extern const uint32_t YUME_PDQ_VERSION_MAJOR;
+extern const uint32_t YUME_PDQ_VERSION_MINOR;
+extern const uint32_t YUME_PDQ_VERSION_PATCH;
+extern const char YUME_PDQ_VERSION_STRING[];
+
+/* include/yume_pdq.h:46-56 / src/lib.rs:85-134: big-endian i8 [dx.0, dx.1, dy.0, dy.1] */
+typedef struct YumePDQ_Dihedrals {
+    uint32_t packed;
+} YumePDQ_Dihedrals;
+
+/* include/yume_pdq.h:62-100 / src/lib.rs:154-177 */
+extern const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_NORMAL;
+extern const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_FLIPPED;
+extern const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_FLOPPED;
+extern const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_ROTATED_180;
+extern const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_ROTATED_90;
+extern const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_ROTATED_270;
+extern const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_ROTATED_90_FLOPPED;
+extern const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_FLOPPED_ROTATED_270;
+
+/* include/yume_pdq.h:44 / src/lib.rs:186-187 */
+typedef bool (*DihedralCallback)(void *ctx, uint32_t dihedral, float threshold, float quality);
+
+/* include/yume_pdq.h:120-125 / src/lib.rs:251-283 (hash_get_threshold, lib.rs:427-455).
+ * input 512*512 f32 row-major; threshold nullable; output 32 bytes; buf1 128*128
+ * f32 (receives the 127x127 tent-filtered image, zero padded); tmp 128 f32
+ * (scratch, left untouched by this implementation); pdqf 256 f32.  Returns the
+ * quality in [0,1]; NaN if no CUDA device is usable (the reference has no error
+ * channel here). Runs on device 0 (or $YUME_PDQ_CUDA_DEVICE). */
+float yume_pdq_hash_smart_kernel(const float *input, float *threshold, uint8_t *output, float *buf1,
+                                 float *tmp, float *pdqf);
+
+/* include/yume_pdq.h:143-147 / src/lib.rs:205-232 (visit_dihedrals, lib.rs:358-420).
+ * Calls `callback` 7 times in the order FLOPPED, ROTATED_180, FLIPPED,
+ * ROTATED_90_FLOPPED, ROTATED_270, FLOPPED_ROTATED_270, ROTATED_90; during each
+ * call `output` holds that dihedral's hash and `pdqf` its transformed PDQF.  The
+ * callback receives the ORIGINAL `threshold` argument every time (lib.rs:223-224).
+ * Returns false iff the callback returned false (or no device is usable); pdqf
+ * is left in the state of the last visited dihedral (C.P^T after all seven). */
+bool yume_pdq_visit_dihedrals_smart_kernel(void *ctx, float threshold, uint8_t *output, float *pdqf,
+                                           DihedralCallback callback);
+
+/* ------------------------------------------------------------------ (B) -- */
+#define YUME_PDQ_CUDA_OK 0
+#define YUME_PDQ_CUDA_E_INVALID (-1)   /* bad argument (NULL, size, q == 0, ...) */
+#define YUME_PDQ_CUDA_E_NO_DEVICE (-2) /* no usable CUDA device / not an sm_100 part */
+#define YUME_PDQ_CUDA_E_CAPACITY (-3)  /* more matches than `cap`; *n_found holds the total */
+#define YUME_PDQ_CUDA_E_NOMEM (-4)
+
+const char *yume_pdq_cuda_error_string(int code);
+int yume_pdq_cuda_device_count(void);
+/* Kernel::ident (src/kernel/mod.rs:429-430) / PDQMatcher::ident (matching/mod.rs:63-64) */
+const char *yume_pdq_cuda_kernel_ident(void);
+const char *yume_pdq_cuda_matcher_ident(void);
+/* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
+uint64_t yume_pdq_cuda_launch_count(void);
+
+/* Order of the 8 dihedral hashes produced per frame:
+ * NORMAL, FLOPPED, ROTATED_180, FLIPPED, ROTATED_90_FLOPPED, ROTATED_270,
+ * FLOPPED_ROTATED_270, ROTATED_90 (NORMAL + the visit order of lib.rs:358-420). */
+extern const uint32_t YUME_PDQ_CUDA_DIHEDRAL_ORDER[8];
+
+/* ---- hasher: fused hot path (hash_get_threshold + visit_dihedrals, batched) ----
+ * frames   n x 512 x 512 f32
+ * hashes   n x 8 x 32 bytes, dihedral order above          (required)
+ * quality  n x 8 f32  (quality of each transformed PDQF)    (nullable)
+ * thresholds n x 8 f32: the threshold each dihedral was quantised with
+ *          (thr0, thr_c, thr_od, thr_r, thr0, thr_c, thr_od, thr_r)  (nullable)
+ * pdqf     n x 256 f32, the untransformed PDQF             (nullable) */
+int yume_pdq_cuda_hash_batch(int device, const float *frames, size_t n, uint8_t *hashes,
+                             float *quality, float *thresholds, float *pdqf, void *stream);
+
+/* ---- hasher: the stages of the `Kernel` trait, batched over n ----
+ * Kernel::jarosz_compress (mod.rs:644-666): frames n x 512 x 512 -> buf1 n x 128 x 128
+ * (127 x 127 valid, padding written as zero, cf. x86.rs:756-757). */
+int yume_pdq_cuda_jarosz_compress(int device, const float *frames, size_t n, float *buf1,
+                                  void *stream);
+/* Kernel::dct2d (mod.rs:543-574): buf1 n x 128 x 128 -> pdqf n x 256 */
+int yume_pdq_cuda_dct2d(int device, const float *buf1, size_t n, float *pdqf, void *stream);
+/* Kernel::sum_of_gradients (mod.rs:617-642) and adjust_quality (mod.rs:611-615);
+ * either output may be NULL. */
+int yume_pdq_cuda_sum_of_gradients(int device, const float *pdqf, size_t n, float *gradient,
+                                   float *quality, void *stream);
+/* Kernel::quantize (mod.rs:595-608, Torben lower median): pdqf n x 256 ->
+ * thresholds n, hashes n x 32 */
+int yume_pdq_cuda_quantize(int device, const float *pdqf, size_t n, float *thresholds,
+                           uint8_t *hashes, void *stream);
+/* kernel::threshold::threshold_2d_f32 (threshold.rs:37-119) */
+int yume_pdq_cuda_threshold_2d_f32(int device, const float *pdqf, size_t n,
+                                   const float *thresholds, uint8_t *hashes, void *stream);
+/* in-place PDQF transforms (mod.rs:345-427; row convention of x86.rs:285-326) */
+#define YUME_PDQ_CUDA_OP_T 0                        /* pdqf_t */
+#define YUME_PDQ_CUDA_OP_NEGATE_ALT_COLS_FALSE 1    /* pdqf_negate_alt_cols::<false>: cols 0,2,.. */
+#define YUME_PDQ_CUDA_OP_NEGATE_ALT_COLS_TRUE 2     /* ::<true>: cols 1,3,.. */
+#define YUME_PDQ_CUDA_OP_NEGATE_ALT_ROWS_TRUE 3     /* pdqf_negate_alt_rows::<true>: rows 0,2,.. */
+#define YUME_PDQ_CUDA_OP_NEGATE_ALT_ROWS_FALSE 4    /* ::<false>: rows 1,3,.. */
+#define YUME_PDQ_CUDA_OP_NEGATE_OFF_DIAGONALS 5     /* pdqf_negate_off_diagonals */
+int yume_pdq_cuda_pdqf_transform(int device, float *pdqf, size_t n, int op, void *stream);
+/* visit_dihedrals (lib.rs:358-420) batched: from pdqf n x 256 and the NORMAL
+ * thresholds thr0[n] produce all 8 hashes / qualities / thresholds as hash_batch does. */
+int yume_pdq_cuda_dihedrals_batch(int device, const float *pdqf, const float *thr0, size_t n,
+                                  uint8_t *hashes, float *quality, float *thresholds,
+                                  void *stream);
+
+/* ---- matcher ------------------------------------------------------------
+ * The haystack lives on the device (like VulkanVectorDatabase, vulkan.rs:40-65);
+ * a query is a set of needles (like VulkanMatcher::scan/find, vulkan.rs:349-472),
+ * but every match is reported (FindsAllMatches = B1 like CpuMatcher,
+ * matching/mod.rs:222). */
+typedef struct YumePDQ_CudaDb YumePDQ_CudaDb;
+
+/* (row, needle, dist): row is the GLOBAL row index (local index + global_row_offset) */
+typedef struct YumePDQ_Match {
+    uint64_t row;
+    uint32_t needle;
+    uint32_t dist;
+} YumePDQ_Match;
+
+/* Upload n_rows x 32 bytes (host or device pointer).  global_row_offset is added
+ * to every reported row so that a row-range shard per GPU reports global rows. */
+int yume_pdq_cuda_db_create(int device, const uint8_t *rows, size_t n_rows,
+                            uint64_t global_row_offset, YumePDQ_CudaDb **out);
+/* Same, but the rows are generated on the device by the counter-based generator
+ * (row r, 64-bit word w = splitmix64(seed + 4r + w), r = global index) --
+ * benches use this for databases that cannot cross PCIe. */
+int yume_pdq_cuda_db_create_synthetic(int device, size_t n_rows, uint64_t global_row_offset,
+                                      uint64_t seed, YumePDQ_CudaDb **out);
+int yume_pdq_cuda_db_destroy(YumePDQ_CudaDb *db);
+size_t yume_pdq_cuda_db_len(const YumePDQ_CudaDb *db);
+int yume_pdq_cuda_db_device(const YumePDQ_CudaDb *db);
+/* device pointer of the resident rows (n_rows x 32 bytes, AoS) */
+const uint8_t *yume_pdq_cuda_db_rows(const YumePDQ_CudaDb *db);
+/* overwrite rows [first, first+n) (host or device source) -- used by tests to plant */
+int yume_pdq_cuda_db_write_rows(YumePDQ_CudaDb *db, size_t first_local_row, const uint8_t *rows,
+                                size_t n);
+
+/* Kernel selection for the matcher (0 = automatic) */
+#define YUME_PDQ_CUDA_ALGO_AUTO 0
+#define YUME_PDQ_CUDA_ALGO_EXACT 1   /* unfiltered: 8 POPC per (row, needle) pair */
+#define YUME_PDQ_CUDA_ALGO_TILED 2   /* rows in registers x needles in smem, 96-bit carry-save prefilter */
+#define YUME_PDQ_CUDA_ALGO_STREAM 3  /* TMA bulk-copy ring + prefilter, needle prefixes in registers (q <= 32) */
+#define YUME_PDQ_CUDA_ALGO_TENSOR 4  /* tcgen05 +-1 formulation for large needle batches (reserved) */
+
+/* PDQMatcher::scan (matching/mod.rs:72-79): *matched = 1 iff any needle is within
+ * `threshold` (inclusive) of any row.  needles q x 32 bytes, host or device. */
+int yume_pdq_cuda_matcher_scan(YumePDQ_CudaDb *db, const uint8_t *needles, size_t q,
+                               uint32_t threshold, int *matched, void *stream);
+/* PDQMatcher::find (matching/mod.rs:84-94) with the callback unrolled into a list:
+ * every (row, needle) with distance <= threshold, sorted by (row, needle) -- the
+ * order in which CpuMatcher::find (matching/mod.rs:336-362) invokes its callback.
+ * At most `cap` entries are written to `out` (host memory); *n_found receives the
+ * total; returns YUME_PDQ_CUDA_E_CAPACITY if it exceeds cap (the first cap entries
+ * in sorted order are still returned). */
+int yume_pdq_cuda_matcher_find(YumePDQ_CudaDb *db, const uint8_t *needles, size_t q,
+                               uint32_t threshold, YumePDQ_Match *out, size_t cap,
+                               size_t *n_found, void *stream);
+/* VulkanMatcher::find semantics (vulkan.rs:408-472): the minimum of
+ * needle + local_row * q over all matches, UINT64_MAX if none. */
+int yume_pdq_cuda_matcher_find_min(YumePDQ_CudaDb *db, const uint8_t *needles, size_t q,
+                                   uint32_t threshold, uint64_t *min_key, void *stream);
+/* Fully device-side, asynchronous on `stream`: needles, out and count are DEVICE
+ * pointers; *count (uint32) must be zeroed by the caller and receives the total
+ * number of matches; the first `cap` (unsorted) are written to out.  `algo`
+ * selects the kernel.  This is what bench.py times. */
+int yume_pdq_cuda_matcher_find_device(YumePDQ_CudaDb *db, const uint8_t *needles_dev, size_t q,
+                                      uint32_t threshold, YumePDQ_Match *out_dev, uint32_t cap,
+                                      uint32_t *count_dev, int algo, void *stream);
+
+/* ---- synthetic inputs (device-side generators shared with the oracle) ----
+ * frames_dev n x 512 x 512 f32 DEVICE pointer. kind 0: uniform 8-bit noise;
+ * kind 1: smooth integer triangle waves + noise (see oracle/pdq_oracle.c). */
+int yume_pdq_cuda_synth_frames(int device, float *frames_dev, size_t n, uint64_t first_frame,
+                               uint64_t seed, int kind, void *stream);
+int yume_pdq_cuda_synth_rows(int device, uint8_t *rows_dev, size_t n_rows, uint64_t first_row,
+                             uint64_t seed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YUME_PDQ_CUDA_H */

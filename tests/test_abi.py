@@ -1,0 +1,76 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every
+symbol include/yume_pdq_cuda.h declares, and FAILS LOUDLY (no CPU fallback) when no
+device is present.  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "yume_pdq_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    funcs = set(re.findall(r"\b(yume_pdq_[a-z0-9_]+)\s*\(", text))
+    data = set(re.findall(r"extern const [^;]*?\b(YUME_PDQ_[A-Z0-9_]+)\s*(?:\[\d*\])?;", text))
+    return funcs, data
+
+
+def test_library_exports_every_declared_symbol(cuda):
+    funcs, data = _declared_symbols()
+    assert len(funcs) >= 25 and len(data) == 13, (sorted(funcs), sorted(data))
+    assert funcs == set(cuda.SIGNATURES)            # the binding covers the header exactly
+    assert data == set(cuda.DATA_SYMBOLS)
+    for name in sorted(funcs | data):
+        assert hasattr(cuda.lib, name), name
+
+
+def test_reference_abi_constants(cuda):
+    # include/yume_pdq.h:22-25 and src/lib.rs:116-133
+    assert C.c_uint32.in_dll(cuda.lib, "YUME_PDQ_VERSION_MAJOR").value == 1
+    assert C.c_uint32.in_dll(cuda.lib, "YUME_PDQ_VERSION_MINOR").value == 1
+    assert C.c_uint32.in_dll(cuda.lib, "YUME_PDQ_VERSION_PATCH").value == 0
+    assert cuda.version() == "1.1.0"
+    D = cuda.Dihedrals
+    assert (D.NORMAL, D.FLIPPED, D.FLOPPED, D.ROTATED_180) == (0x01000001, 0x010000FF, 0xFF000001,
+                                                                 0xFF0000FF)
+    assert (D.ROTATED_90, D.ROTATED_270, D.ROTATED_90_FLOPPED, D.FLOPPED_ROTATED_270) == (
+        0x0001FF00, 0x00010100, 0x00FFFF00, 0x00FF0100)
+    assert D.into_tuples(D.ROTATED_90) == ((0, 1), (-1, 0))
+    assert D.from_tuples((0, -1), (1, 0)) == D.FLOPPED_ROTATED_270
+    assert cuda.DIHEDRAL_ORDER == [D.NORMAL, D.FLOPPED, D.ROTATED_180, D.FLIPPED, D.ROTATED_90_FLOPPED,
+                                   D.ROTATED_270, D.FLOPPED_ROTATED_270, D.ROTATED_90]
+
+
+def test_dihedral_order_matches_oracle(cuda, oracle):
+    assert cuda.DIHEDRAL_ORDER == oracle.dihedral_order
+
+
+def test_no_cpu_fallback(cuda):
+    if cuda.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    frames = np.zeros((1, 512, 512), dtype=np.float32)
+    with pytest.raises(cuda.YumePdqCudaError) as e:
+        cuda.CudaKernel().hash_batch(frames)
+    assert e.value.code == cuda.E_NO_DEVICE
+    with pytest.raises(cuda.YumePdqCudaError):
+        cuda.CudaVectorDatabase(np.zeros((4, 32), dtype=np.uint8))
+    with pytest.raises(cuda.YumePdqCudaError):
+        cuda.hash_get_threshold(frames[0])      # the reference ABI returns NaN -> raised here
+    assert cuda.visit_dihedrals(np.zeros((16, 16), dtype=np.float32), 0.0, lambda *a: True) is False
+
+
+def test_product_never_imports_oracle():
+    """The product package must not reference oracle/ in any way."""
+    pkg = os.path.join(ROOT, "yume_pdq_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                for line in text.splitlines():
+                    code = line.split("//")[0].split("#")[0] if not f.endswith(".py") else line.split("#")[0]
+                    assert "import oracle" not in code and "from oracle" not in code, (f, line)
+                    assert "liboracle" not in code and "libcpu_baseline" not in code, (f, line)

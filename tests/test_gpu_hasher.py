@@ -1,0 +1,196 @@
+"""GPU parity of the hasher against the CPU oracle, through the C ABI.
+The CUDA kernels follow the scalar reference kernel's summation order, so the bar here
+is BIT-EXACT (stronger than north_star's 1e-4 relative / 2-bit tolerance, which is
+asserted as well for the record)."""
+import numpy as np
+import pytest
+
+from conftest import hamming
+from oracle import pyoracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def kernel(cuda):
+    assert cuda.device_count() > 0, "no CUDA device: the product has no CPU fallback"
+    return cuda.CudaKernel(0)
+
+
+def _assert_same_hash_outputs(got, want_h, want_q, want_t, want_p):
+    assert (np.asarray(got["hashes"]) == want_h).all()
+    assert np.array_equal(np.asarray(got["pdqf"]).view(np.uint32), want_p.view(np.uint32))
+    assert np.array_equal(np.asarray(got["quality"]), want_q)
+    assert np.array_equal(np.asarray(got["thresholds"]), want_t)
+
+
+def test_kats_bit_exact(kernel, oracle, kat, aaa_luma):
+    frames = np.stack([aaa_luma, pyoracle.readme_doctest_frame()])
+    got = kernel.hash_batch(frames, want_pdqf=True)
+    # reference golden vectors first
+    assert got["hashes"][0, 0].tobytes().hex() in kat["aaa_orig_expect"]
+    assert hamming(got["hashes"][1, 0], bytes.fromhex(kat["readme_doctest_hash"])) <= 2
+    assert np.abs(got["pdqf"][1] - np.array(kat["readme_doctest_pdqf_1dp"])).max() <= 0.0501
+    # then the oracle, bit for bit, all 8 dihedrals
+    _assert_same_hash_outputs(got, *oracle.hash_all_dihedrals(frames))
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+def test_synthetic_frames_bit_exact(cuda, kernel, oracle, kind):
+    import torch
+    n = 48
+    dev = torch.empty((n, 512, 512), dtype=torch.float32, device="cuda:0")
+    cuda.synth_frames(dev, n, first_frame=1000, kind=kind)
+    torch.cuda.synchronize()
+    host = oracle.synth_frames(n, first_frame=1000, kind=kind)
+    assert np.array_equal(dev.cpu().numpy(), host)          # generators agree exactly
+    got = kernel.hash_batch(dev, want_pdqf=True)
+    torch.cuda.synchronize()
+    got = {k: v.cpu().numpy() for k, v in got.items()}
+    want_h, want_q, want_t, want_p = oracle.hash_all_dihedrals(host)
+    _assert_same_hash_outputs(got, want_h, want_q, want_t, want_p)
+    # north_star tolerance, for the record
+    floor = 1e-3 * np.abs(want_p).max()
+    rel = np.abs(got["pdqf"] - want_p) / np.maximum(np.abs(want_p), floor)
+    assert rel.max() <= 1e-4
+    if kind == 1:
+        assert (want_q > 0.5).mean() > 0.9     # the smooth generator gives usable frames
+
+
+def test_host_path_double_buffering(kernel, oracle):
+    # > 64 frames: exercises the chunked H2D pipeline of the host-pointer path
+    host = oracle.synth_frames(70, first_frame=5, kind=1)
+    got = kernel.hash_batch(host, want_pdqf=True)
+    idx = [0, 1, 63, 64, 65, 69]
+    want_h, want_q, want_t, want_p = oracle.hash_all_dihedrals(host[idx])
+    assert (got["hashes"][idx] == want_h).all()
+    assert np.array_equal(got["pdqf"][idx], want_p)
+    assert np.array_equal(got["quality"][idx], want_q)
+    # optional outputs may be omitted
+    only = kernel.hash_batch(host[:3], want_quality=False, want_thresholds=False)
+    assert only["quality"] is None and (only["hashes"] == got["hashes"][:3]).all()
+
+
+def test_edge_frames(kernel, oracle):
+    rng = np.random.default_rng(3)
+    frames = np.zeros((6, 512, 512), dtype=np.float32)
+    frames[1] = 255.0                                     # constant: all PDQF ~ 0, quality 0
+    frames[2] = rng.random((512, 512), dtype=np.float32)  # the reference bench input, uniform [0,1)
+    frames[3] = np.arange(512, dtype=np.float32)[None, :]  # horizontal ramp
+    frames[4] = np.arange(512, dtype=np.float32)[:, None]  # vertical ramp
+    frames[5] = (rng.integers(0, 2, (512, 512)) * 255).astype(np.float32)
+    got = kernel.hash_batch(frames, want_pdqf=True)
+    _assert_same_hash_outputs(got, *oracle.hash_all_dihedrals(frames))
+    assert kernel.hash_batch(frames[:0])["hashes"].shape == (0, 8, 32)   # empty batch
+
+
+def test_stage_entry_points(kernel, oracle, aaa_luma):
+    """Each `Kernel` trait method on its own."""
+    host = np.concatenate([aaa_luma[None], oracle.synth_frames(3, kind=1)])
+    n = host.shape[0]
+    buf1 = kernel.jarosz_compress(host)
+    want_buf1 = np.stack([oracle.jarosz_compress(f) for f in host])
+    assert np.array_equal(buf1.view(np.uint32), want_buf1.view(np.uint32))
+    assert (buf1[:, 127, :] == 0).all() and (buf1[:, :, 127] == 0).all()
+    pdqf = kernel.dct2d(buf1)
+    want_pdqf = np.stack([oracle.dct2d(b) for b in want_buf1])
+    assert np.array_equal(pdqf.view(np.uint32), want_pdqf.view(np.uint32))
+    g, q = kernel.sum_of_gradients(pdqf, quality=True)
+    want_g = np.array([oracle.sum_of_gradients(p) for p in want_pdqf], dtype=np.float32)
+    assert np.array_equal(g, want_g)
+    assert np.array_equal(q, np.array([oracle.adjust_quality(x) for x in want_g], dtype=np.float32))
+    h, thr = kernel.quantize(pdqf)
+    for i in range(n):
+        wh, wt = oracle.quantize(want_pdqf[i])
+        assert (h[i] == wh).all() and thr[i] == np.float32(wt)
+    # KAT-5 re-threshold identity (lib.rs:659-687) on the device
+    assert (kernel.threshold_2d_f32(pdqf, thr) == h).all()
+    thr2 = np.array([0.0, 1.5, -3.0, 100.0], dtype=np.float32)
+    h2 = kernel.threshold_2d_f32(pdqf, thr2)
+    for i in range(n):
+        assert (h2[i] == oracle.threshold_2d_f32(want_pdqf[i], float(thr2[i]))).all()
+    # transforms
+    P = want_pdqf
+    assert np.array_equal(kernel.pdqf_t(P.copy()), np.stack([oracle.pdqf_t(p) for p in P]))
+    for neg in (False, True):
+        assert np.array_equal(kernel.pdqf_negate_alt_cols(P.copy(), neg),
+                              np.stack([oracle.negate_alt_cols(p, neg) for p in P]))
+        assert np.array_equal(kernel.pdqf_negate_alt_rows(P.copy(), neg),
+                              np.stack([oracle.negate_alt_rows(p, neg) for p in P]))
+    assert np.array_equal(kernel.pdqf_negate_off_diagonals(P.copy()),
+                          np.stack([oracle.negate_off_diagonals(p) for p in P]))
+    # visit_dihedrals batched
+    d = kernel.dihedrals_batch(pdqf, thr)
+    want_h, want_q, want_t, _ = oracle.hash_all_dihedrals(host)
+    assert (d["hashes"] == want_h).all()
+    assert np.array_equal(d["quality"], want_q) and np.array_equal(d["thresholds"], want_t)
+
+
+def test_quantize_ties_and_median(kernel, oracle):
+    rng = np.random.default_rng(9)
+    P = rng.standard_normal((64, 16, 16)).astype(np.float32)
+    P[:32] = np.round(P[:32] * 2) / 2          # heavy ties around the median
+    P[0] = 0.0                                  # all equal
+    P[1, :8] = -0.0                             # signed zeros
+    h, thr = kernel.quantize(P)
+    for i in range(P.shape[0]):
+        wh, wt = oracle.quantize(P[i])
+        assert thr[i] == np.float32(wt), i       # == treats -0.0 and 0.0 alike
+        assert (h[i] == wh).all(), i
+        assert thr[i] == np.sort(P[i].ravel())[127]
+
+
+def test_reference_two_function_abi(cuda, oracle, aaa_luma):
+    """yume_pdq_hash_smart_kernel / yume_pdq_visit_dihedrals_smart_kernel (include/yume_pdq.h)."""
+    q, thr, h, pdqf, buf1 = cuda.hash_get_threshold(aaa_luma)
+    oq, othr, oh, opdqf = oracle.hash_get_threshold(aaa_luma)
+    assert (q, thr) == (oq, othr) and (h == oh).all() and np.array_equal(pdqf, opdqf)
+    assert np.array_equal(buf1, oracle.jarosz_compress(aaa_luma))
+    ok, want, final = oracle.visit_dihedrals(opdqf, othr)
+    seen = []
+    p = pdqf.copy()
+    assert cuda.visit_dihedrals(p, thr, lambda d, t, qq, pv, hv: seen.append(
+        (d, t, qq, hv.copy(), pv.copy())) or True)
+    assert len(seen) == 7
+    for (d, t, qq, hv, pv), (od, ot, oq_, oh_, op_) in zip(seen, want):
+        assert d == od and qq == oq_ and (hv == oh_).all() and np.array_equal(pv, op_)
+        assert t == thr                      # lib.rs:223-224: the ORIGINAL threshold is forwarded
+    assert np.array_equal(p, final)
+    # early stop after 3 callbacks
+    seen2 = []
+    p2 = pdqf.copy()
+    assert cuda.visit_dihedrals(p2, thr, lambda *a: (seen2.append(a[0]) or len(seen2) < 3)) is False
+    assert len(seen2) == 3 and np.array_equal(p2, want[2][4])
+    assert cuda.hash_float(aaa_luma)[0] == oq and (cuda.hash(aaa_luma)[1] == oh).all()
+
+
+def test_full_size_batch_properties(cuda, kernel, oracle):
+    """BASELINE config 2: 4096 frames on the device.  Size-independent properties +
+    an oracle spot check on a seeded sample."""
+    import torch
+    n = 4096
+    dev = torch.empty((n, 512, 512), dtype=torch.float32, device="cuda:0")
+    cuda.synth_frames(dev, n, first_frame=0, kind=1)
+    a = kernel.hash_batch(dev, want_pdqf=True)
+    b = kernel.hash_batch(dev, want_pdqf=True)
+    torch.cuda.synchronize()
+    for k in a:                                   # deterministic / idempotent
+        assert torch.equal(a[k], b[k]), k
+    hashes = a["hashes"].cpu().numpy()
+    # every NORMAL hash has exactly 128 or fewer bits set (strict > lower median)
+    bits = np.unpackbits(hashes[:, 0, :], axis=1).sum(axis=1)
+    assert (bits <= 128).all() and (bits >= 100).mean() > 0.99
+    # frequency-domain FLOPPED/FLIPPED dihedrals ~ hashing the mirrored frames (image space)
+    sub = slice(0, 64)
+    flop = kernel.hash_batch(torch.flip(dev[sub], dims=[2]).contiguous())["hashes"].cpu().numpy()
+    flip = kernel.hash_batch(torch.flip(dev[sub], dims=[1]).contiguous())["hashes"].cpu().numpy()
+    d_flop = [hamming(flop[i, 0], hashes[i, 1]) for i in range(64)]
+    d_flip = [hamming(flip[i, 0], hashes[i, 3]) for i in range(64)]
+    assert np.median(d_flop) <= 16 and np.median(d_flip) <= 16, (d_flop, d_flip)
+    # oracle spot check
+    idx = np.random.default_rng(0).choice(n, size=24, replace=False)
+    host = dev[torch.from_numpy(idx).cuda()].cpu().numpy()
+    want_h, want_q, want_t, want_p = oracle.hash_all_dihedrals(host)
+    assert (hashes[idx] == want_h).all()
+    assert np.array_equal(a["pdqf"].cpu().numpy()[idx], want_p)
+    assert np.array_equal(a["quality"].cpu().numpy()[idx], want_q)

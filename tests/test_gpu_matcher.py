@@ -1,0 +1,189 @@
+"""GPU parity of the matcher against the CPU oracle (bit-exact match sets), through the
+C ABI: KAT-4 planted positives, inclusive boundary, every kernel variant, ragged sizes."""
+import numpy as np
+import pytest
+
+from helpers import flip_bits, flip_bits_with_replacement, match_tuples, plant
+
+pytestmark = pytest.mark.gpu
+
+
+def _find_device(cuda, matcher, needles, algo, cap=1 << 16):
+    import torch
+    q = needles.shape[0]
+    nd = torch.from_numpy(needles).cuda()
+    out = torch.zeros((cap, 16), dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    matcher.find_device(nd, q, out, cap, cnt, algo=algo)
+    torch.cuda.synchronize()
+    n = int(cnt.item())
+    assert n <= cap
+    m = out[:n].cpu().numpy().view(cuda.MATCH_DTYPE).reshape(-1)
+    return sorted(match_tuples(m))
+
+
+@pytest.mark.parametrize("n_rows", [1, 511, 4096, 100_003])
+@pytest.mark.parametrize("q", [1, 8, 13, 32, 40])
+def test_planted_vs_oracle_all_algos(cuda, oracle, n_rows, q):
+    rng = np.random.default_rng(n_rows * 131 + q)
+    rows = oracle.synth_db(n_rows, first_row=77)
+    needles = rng.integers(0, 256, size=(q, 32), dtype=np.uint8)
+    if n_rows >= 6 * q:
+        plant(rows, needles, [0, 15, 30, 31, 32, 33], rng)
+    else:
+        rows[0] = flip_bits(needles[q - 1], 31, rng)
+    want = match_tuples(oracle.matcher_find(rows, needles, 31))
+    db = cuda.CudaVectorDatabase(rows)
+    m = cuda.CudaMatcher(db, 31)
+    assert match_tuples(m.find_all(needles)) == want          # sorted (row, needle) like CpuMatcher::find
+    assert m.scan(needles) == (len(want) > 0)
+    assert m.find_min(needles) == oracle.matcher_find_min(rows, needles, 31)
+    for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_STREAM):
+        assert _find_device(cuda, m, needles, algo) == sorted(want), algo
+    db.close()
+
+
+@pytest.mark.parametrize("threshold", [0, 1, 30, 31, 32, 40, 41, 64, 128, 256])
+def test_thresholds(cuda, oracle, threshold):
+    rng = np.random.default_rng(threshold)
+    rows = oracle.synth_db(20_000)
+    needles = rng.integers(0, 256, size=(8, 32), dtype=np.uint8)
+    dists = sorted({0, max(threshold - 1, 0), threshold, min(threshold + 1, 256)} & set(range(257)))
+    plant(rows, needles, dists, rng)
+    want = match_tuples(oracle.matcher_find(rows, needles, threshold))
+    db = cuda.CudaVectorDatabase(rows)
+    m = cuda.CudaMatcher(db, threshold)
+    if len(want) < 200_000:
+        assert match_tuples(m.find_all(needles, cap=1 << 18)) == want
+    else:   # threshold 128/256 match (nearly) everything: compare counts and a prefix
+        got = m.find_all(needles, cap=1 << 18)
+        assert len(got) == len(want) and match_tuples(got[:1000]) == want[:1000]
+    if threshold <= 40:
+        for algo in (cuda.ALGO_TILED, cuda.ALGO_STREAM):
+            assert _find_device(cuda, m, needles, algo, cap=1 << 18) == sorted(want)
+    db.close()
+
+
+def test_reference_planted_positive_procedure(cuda, oracle):
+    """matching/mod.rs:460-538: 2048 random rows, 8/16/24 needles, no match; then plant a copy with
+    31 random flips at every slot (subsampled) and require scan + find -> (row, needle)."""
+    rng = np.random.default_rng(0x79756D65)
+    rows = rng.integers(0, 256, size=(2048, 32), dtype=np.uint8)
+    for q in (8, 16, 24):
+        needles = rng.integers(0, 256, size=(q, 32), dtype=np.uint8)
+        db = cuda.CudaVectorDatabase(rows)
+        m = cuda.CudaMatcher(db, 31)
+        assert not m.scan(needles) and len(m.find_all(needles)) == 0 and m.find_min(needles) is None
+        for i in range(0, 2048, 331):
+            for j in range(0, q, 3):
+                db.write_rows(i, flip_bits_with_replacement(needles[j], 31, rng)[None])
+                assert m.scan(needles)
+                assert m.find(needles, lambda r, n: (r, n)) == (i, j)
+                assert m.find_min(needles) == (i, j)
+                db.write_rows(i, rows[i][None])
+        db.close()
+
+
+def test_large_needle_batch_multi_chunk(cuda, oracle):
+    """q > 2048 spans several needle chunks of the tiled kernel (the INT-pipe regime)."""
+    rng = np.random.default_rng(21)
+    q = 5000
+    rows = oracle.synth_db(30_011, first_row=10**9)
+    needles = rng.integers(0, 256, size=(q, 32), dtype=np.uint8)
+    sel = rng.choice(q, size=300, replace=False)
+    pos = rng.choice(rows.shape[0], size=300, replace=False)
+    for j, r in zip(sel, pos):
+        rows[r] = flip_bits(needles[j], int(rng.integers(0, 34)), rng)
+    want = match_tuples(oracle.matcher_find(rows, needles, 31))
+    assert len(want) > 200
+    db = cuda.CudaVectorDatabase(rows)
+    m = cuda.CudaMatcher(db, 31)
+    assert match_tuples(m.find_all(needles)) == want
+    assert _find_device(cuda, m, needles, cuda.ALGO_EXACT) == sorted(want)
+    db.close()
+
+
+def test_adversarial_dense_matches(cuda, oracle):
+    """Near-duplicate database: every prefix filter survives, the candidate queue of the tiled kernel
+    overflows, the output list overflows the first capacity guess.  Correctness must not depend on
+    the data."""
+    rng = np.random.default_rng(4)
+    base = rng.integers(0, 256, size=32, dtype=np.uint8)
+    rows = np.stack([flip_bits(base, int(rng.integers(0, 40)), rng) for _ in range(6000)])
+    needles = np.stack([flip_bits(base, int(rng.integers(0, 6)), rng) for _ in range(64)])
+    want = match_tuples(oracle.matcher_find(rows, needles, 31))
+    assert len(want) > 100_000
+    db = cuda.CudaVectorDatabase(rows)
+    m = cuda.CudaMatcher(db, 31)
+    got = m.find_all(needles, cap=1000)        # forces the E_CAPACITY retry path
+    assert match_tuples(got) == want
+    for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED):
+        assert _find_device(cuda, m, needles, algo, cap=1 << 19) == sorted(want)
+    assert _find_device(cuda, m, needles[:32], cuda.ALGO_STREAM, cap=1 << 19) == sorted(
+        t for t in want if t[1] < 32)
+    # capacity error contract of the C ABI: first `cap` entries in sorted order + total
+    import ctypes as C
+    out = np.zeros(10, dtype=cuda.MATCH_DTYPE)
+    n = C.c_size_t(0)
+    rc = cuda.lib.yume_pdq_cuda_matcher_find(db._h, cuda._ptr(needles), 64, 31, cuda._ptr(out), 10,
+                                             C.byref(n), None)
+    assert rc == cuda.E_CAPACITY and n.value == len(want) and match_tuples(out) == want[:10]
+    db.close()
+
+
+def test_global_row_offset_and_empty(cuda, oracle):
+    rng = np.random.default_rng(8)
+    rows = oracle.synth_db(5000)
+    needles = rng.integers(0, 256, size=(8, 32), dtype=np.uint8)
+    plant(rows, needles, [3, 31], rng)
+    want = match_tuples(oracle.matcher_find(rows, needles, 31))
+    off = 3_000_000_000
+    db = cuda.CudaVectorDatabase(rows, global_row_offset=off)
+    m = cuda.CudaMatcher(db, 31)
+    assert match_tuples(m.find_all(needles)) == [(r + off, j, d) for r, j, d in want]
+    assert m.find_min(needles) == oracle.matcher_find_min(rows, needles, 31)   # local row, like Vulkan
+    db.close()
+    empty = cuda.CudaVectorDatabase(np.zeros((0, 32), dtype=np.uint8))
+    assert len(empty) == 0 and not cuda.CudaMatcher(empty, 31).scan(needles)
+    assert len(cuda.CudaMatcher(empty, 31).find_all(needles)) == 0
+    with pytest.raises(cuda.YumePdqCudaError):
+        cuda.CudaMatcher(db if False else empty, 31).find_all(needles[:0])    # q == 0 is invalid
+
+
+def test_headline_config_10m(cuda, oracle):
+    """BASELINE config 3: 10,000,384-row synthetic DB (benches/matcher.rs:18-24), 8 needles,
+    threshold 31: random needles do not match (benches/matcher.rs:79 asserts !matched); ~100
+    planted rows are found exactly -- by every kernel variant."""
+    n = (10_000_000 // 2048 + 1) * 2048
+    rng = np.random.default_rng(31)
+    db = cuda.CudaVectorDatabase(synthetic_rows=n, seed=0x79756D652D706471)
+    assert len(db) == n
+    # the device generator equals the oracle generator (slice check)
+    import torch
+    base = torch.empty(0)
+    sl = oracle.synth_db(4096, first_row=n - 4096)
+    import ctypes as C
+    buf = np.zeros((4096, 32), dtype=np.uint8)
+    torch.cuda.synchronize()
+    t = torch.zeros((4096, 32), dtype=torch.uint8, device="cuda")
+    cuda.synth_rows(t, 4096, first_row=n - 4096)
+    torch.cuda.synchronize()
+    assert np.array_equal(t.cpu().numpy(), sl)
+    needles = rng.integers(0, 256, size=(8, 32), dtype=np.uint8)
+    m = cuda.CudaMatcher(db, 31)
+    assert not m.scan(needles)
+    planted = []
+    for r in rng.choice(n, size=104, replace=False):
+        j = int(rng.integers(0, 8))
+        d = int(rng.choice([0, 7, 30, 31, 32, 33, 40]))
+        db.write_rows(int(r), flip_bits(needles[j], d, rng)[None])
+        planted.append((int(r), j, d))
+    want = sorted(p for p in planted if p[2] <= 31)
+    assert match_tuples(m.find_all(needles)) == want
+    assert m.find_min(needles) == (want[0][0], want[0][1])
+    for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_STREAM):
+        assert _find_device(cuda, m, needles, algo) == want
+    # last rows of the last chunk are planted too (tail handling)
+    db.write_rows(n - 1, needles[5][None])
+    assert match_tuples(m.find_all(needles))[-1] == (n - 1, 5, 0)
+    db.close()

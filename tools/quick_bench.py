@@ -1,0 +1,81 @@
+"""Developer micro-benchmarks (not the contract bench): CUDA-event timings of the individual kernels."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import yume_pdq_b200 as yp
+
+
+def timeit(fn, iters=20, warm=3, flush=None):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    what = sys.argv[1:] or ["scan", "hash", "tiled"]
+    torch.cuda.init()
+    print(torch.cuda.get_device_name(0))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    rng = np.random.default_rng(0)
+    if "scan" in what:
+        n = (10_000_000 // 2048 + 1) * 2048
+        db = yp.CudaVectorDatabase(synthetic_rows=n)
+        m = yp.CudaMatcher(db, 31)
+        out = torch.zeros((1 << 16, 16), dtype=torch.uint8, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for q in (8, 16, 32):
+            needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
+            for name, algo in (("exact", yp.ALGO_EXACT), ("tiled", yp.ALGO_TILED), ("stream", yp.ALGO_STREAM)):
+                med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 16, cnt, algo=algo), flush=flush)
+                print(f"scan 10M x {q:3d} {name:7s}: median {med:8.1f} us  best {best:8.1f} us  "
+                      f"{n * 32 / med / 1e3:7.1f} GB/s  {n * q / med / 1e6:8.3f} Tpairs/s  hits={int(cnt.item())}")
+                cnt.zero_()
+        db.close()
+    if "tiled" in what:
+        n = (10_000_000 // 2048 + 1) * 2048
+        db = yp.CudaVectorDatabase(synthetic_rows=n)
+        m = yp.CudaMatcher(db, 31)
+        out = torch.zeros((1 << 20, 16), dtype=torch.uint8, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for q in (1024, 8192, 32768):
+            needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
+            for name, algo in (("tiled", yp.ALGO_TILED),) + ((("exact", yp.ALGO_EXACT),) if q <= 8192 else ()):
+                med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 20, cnt, algo=algo), iters=3, warm=1)
+                print(f"match 10M x {q:6d} {name:6s}: median {med / 1e3:9.2f} ms  {n * q / med / 1e6:8.3f} Tpairs/s  "
+                      f"hits={int(cnt.item())}")
+                cnt.zero_()
+        db.close()
+    if "hash" in what:
+        k = yp.CudaKernel(0)
+        for n in (592, 4096):
+            frames = torch.empty((n, 512, 512), dtype=torch.float32, device="cuda")
+            yp.synth_frames(frames, n, kind=1)
+            outs = {"hashes": torch.empty((n, 8, 32), dtype=torch.uint8, device="cuda"),
+                    "quality": torch.empty((n, 8), dtype=torch.float32, device="cuda"),
+                    "thresholds": torch.empty((n, 8), dtype=torch.float32, device="cuda")}
+            med, best = timeit(lambda: k.hash_batch(frames, out=outs), iters=10, flush=flush)
+            print(f"hash {n:5d} frames: median {med:9.1f} us  best {best:9.1f} us  {n / med:7.3f} Mimg/s  "
+                  f"{n * 1048576 / med / 1e3:7.1f} GB/s")
+            del frames
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,801 @@
+// api.cu -- the extern "C" boundary (include/yume_pdq_cuda.h).
+//
+// Host-side plumbing only: argument checks, host<->device staging (pinned,
+// double-buffered for frame batches), per-handle scratch for the matcher, result
+// sorting.  All arithmetic on frames / PDQFs / hashes happens in the kernels of
+// hasher.cu and matcher.cu; there is no CPU fallback.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ypdq {
+
+std::atomic<uint64_t> g_launches{0};
+
+int ensure_device(int device)
+{
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        (void)cudaGetLastError();
+        return YUME_PDQ_CUDA_E_NO_DEVICE;
+    }
+    if (device < 0 || device >= count)
+        return YUME_PDQ_CUDA_E_INVALID;
+    static std::atomic<int> checked[64];
+    if (device < 64 && checked[device].load() == 0) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess ||
+            major != 10) {
+            (void)cudaGetLastError();
+            return YUME_PDQ_CUDA_E_NO_DEVICE;  // the fatbin holds sm_100a code only
+        }
+        checked[device].store(1);
+    }
+    YPDQ_CUDA_TRY(cudaSetDevice(device));
+    return 0;
+}
+
+namespace {
+
+// grow-only device / pinned scratch, one set per host thread and device
+struct Scratch {
+    void *dev = nullptr;
+    size_t dev_bytes = 0;
+    void *pin = nullptr;
+    size_t pin_bytes = 0;
+    int device = -1;
+    int reserve(int device_, size_t d, size_t p)
+    {
+        if (device != device_) {  // other device: drop (the old allocations stay with their device)
+            dev = pin = nullptr;
+            dev_bytes = pin_bytes = 0;
+            device = device_;
+        }
+        if (d > dev_bytes) {
+            if (dev)
+                cudaFree(dev);
+            dev = nullptr;
+            dev_bytes = 0;
+            cudaError_t e = cudaMalloc(&dev, d);
+            if (e != cudaSuccess) {
+                (void)cudaGetLastError();
+                return e == cudaErrorMemoryAllocation ? YUME_PDQ_CUDA_E_NOMEM : (int)e;
+            }
+            dev_bytes = d;
+        }
+        if (p > pin_bytes) {
+            if (pin)
+                cudaFreeHost(pin);
+            pin = nullptr;
+            pin_bytes = 0;
+            cudaError_t e = cudaMallocHost(&pin, p);
+            if (e != cudaSuccess) {
+                (void)cudaGetLastError();
+                return YUME_PDQ_CUDA_E_NOMEM;
+            }
+            pin_bytes = p;
+        }
+        return 0;
+    }
+};
+
+Scratch &tls_scratch(int which)
+{
+    static thread_local Scratch s[4];
+    return s[which];
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Carves device sub-buffers for host-resident arguments out of one Scratch allocation.
+struct Stager {
+    cudaStream_t s;
+    struct Out {
+        void *host;
+        const void *dev;
+        size_t bytes;
+    };
+    std::vector<Out> outs;
+    uint8_t *base = nullptr;
+    size_t off = 0;
+    explicit Stager(cudaStream_t s_) : s(s_) {}
+    template <class T>
+    int in(const T *p, size_t bytes, const T **dp)
+    {
+        if (!p || is_device_ptr(p)) {
+            *dp = p;
+            return 0;
+        }
+        T *d = reinterpret_cast<T *>(base + off);
+        off += align_up(bytes, 256);
+        YPDQ_CUDA_TRY(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, s));
+        *dp = d;
+        return 0;
+    }
+    template <class T>
+    void out(T *p, size_t bytes, T **dp)
+    {
+        if (!p || is_device_ptr(p)) {
+            *dp = p;
+            return;
+        }
+        T *d = reinterpret_cast<T *>(base + off);
+        off += align_up(bytes, 256);
+        outs.push_back({p, d, bytes});
+        *dp = d;
+    }
+    int finish()
+    {
+        for (auto &o : outs)
+            YPDQ_CUDA_TRY(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, s));
+        if (!outs.empty())
+            YPDQ_CUDA_TRY(cudaStreamSynchronize(s));
+        return 0;
+    }
+};
+
+template <class T>
+inline size_t host_bytes(const T *p, size_t bytes)
+{
+    return (p && !is_device_ptr(p)) ? align_up(bytes, 256) : 0;
+}
+
+__global__ void dihedral_states_kernel(const float *__restrict__ pdqf, float *__restrict__ states)
+{
+    // states[d-1][i][j], d = 1..7, same sign/transposition table as hasher.cu:dihedral_value
+    const int tid = threadIdx.x, i = tid >> 4, j = tid & 15;
+    for (int d = 1; d < 8; d++) {
+        float v = (d & 4) ? pdqf[j * 16 + i] : pdqf[i * 16 + j];
+        const bool c = (0xC6 >> d) & 1, r = (0x6C >> d) & 1;
+        const bool neg = (c && !(j & 1)) != (r && !(i & 1));
+        states[(d - 1) * 256 + tid] = neg ? -v : v;
+    }
+}
+
+int default_device()
+{
+    const char *e = std::getenv("YUME_PDQ_CUDA_DEVICE");
+    return e ? std::atoi(e) : 0;
+}
+
+constexpr uint32_t dih(int dx0, int dx1, int dy0, int dy1)
+{
+    return (uint32_t)(uint8_t)dx0 << 24 | (uint32_t)(uint8_t)dx1 << 16 | (uint32_t)(uint8_t)dy0 << 8 |
+           (uint32_t)(uint8_t)dy1;
+}
+
+}  // namespace
+}  // namespace ypdq
+
+using namespace ypdq;
+
+struct YumePDQ_CudaDb {
+    int device = 0;
+    int sm_count = 148;
+    uint8_t *rows = nullptr;
+    size_t n_rows = 0;
+    uint64_t offset = 0;
+    // per-handle scratch for the host-facing calls
+    uint8_t *d_needles = nullptr;
+    size_t needles_cap = 0;
+    YumePDQ_Match *d_out = nullptr;
+    size_t out_cap = 0;
+    uint32_t *d_count = nullptr;           // [0] count, then 8-byte aligned min key at +8
+    unsigned long long *d_min = nullptr;
+    void *h_pin = nullptr;                 // 16 bytes pinned: count + min key
+    std::mutex mu;
+};
+
+extern "C" {
+
+/* ---- (A) reference ABI -------------------------------------------------- */
+const uint32_t YUME_PDQ_VERSION_MAJOR = 1;
+const uint32_t YUME_PDQ_VERSION_MINOR = 1;
+const uint32_t YUME_PDQ_VERSION_PATCH = 0;
+const char YUME_PDQ_VERSION_STRING[] = "1.1.0";
+
+/* src/lib.rs:116-133 */
+const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_NORMAL = {dih(1, 0, 0, 1)};
+const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_FLIPPED = {dih(1, 0, 0, -1)};
+const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_FLOPPED = {dih(-1, 0, 0, 1)};
+const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_ROTATED_180 = {dih(-1, 0, 0, -1)};
+const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_ROTATED_90 = {dih(0, 1, -1, 0)};
+const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_ROTATED_270 = {dih(0, 1, 1, 0)};
+const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_ROTATED_90_FLOPPED = {dih(0, -1, -1, 0)};
+const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_FLOPPED_ROTATED_270 = {dih(0, -1, 1, 0)};
+
+const uint32_t YUME_PDQ_CUDA_DIHEDRAL_ORDER[8] = {
+    dih(1, 0, 0, 1),  dih(-1, 0, 0, 1), dih(-1, 0, 0, -1), dih(1, 0, 0, -1),
+    dih(0, -1, -1, 0), dih(0, 1, 1, 0),  dih(0, -1, 1, 0),  dih(0, 1, -1, 0),
+};
+
+float yume_pdq_hash_smart_kernel(const float *input, float *threshold, uint8_t *output, float *buf1,
+                                 float *tmp, float *pdqf)
+{
+    (void)tmp;  // scratch in the reference; not needed here and left untouched
+    const int device = default_device();
+    if (!input || !output || !buf1 || !pdqf || ensure_device(device) != 0)
+        return std::numeric_limits<float>::quiet_NaN();
+    // hash_get_threshold, src/lib.rs:427-455
+    uint8_t hashes[256];
+    float quality[8], thr[8];
+    if (yume_pdq_cuda_jarosz_compress(device, input, 1, buf1, nullptr) != 0 ||
+        yume_pdq_cuda_hash_batch(device, input, 1, hashes, quality, thr, pdqf, nullptr) != 0)
+        return std::numeric_limits<float>::quiet_NaN();
+    std::memcpy(output, hashes, 32);
+    if (threshold)
+        *threshold = thr[0];
+    return quality[0];
+}
+
+bool yume_pdq_visit_dihedrals_smart_kernel(void *ctx, float threshold, uint8_t *output, float *pdqf,
+                                           DihedralCallback callback)
+{
+    const int device = default_device();
+    if (!output || !pdqf || !callback || ensure_device(device) != 0)
+        return false;
+    Scratch &sc = tls_scratch(1);
+    if (sc.reserve(device, 16 * 1024, 16 * 1024) != 0)
+        return false;
+    float *d_p = reinterpret_cast<float *>(sc.dev);
+    float *d_states = d_p + 256;
+    float *d_thr0 = d_states + 7 * 256;
+    float *d_quality = d_thr0 + 64;
+    uint8_t *d_hashes = reinterpret_cast<uint8_t *>(d_quality + 64);
+    cudaStream_t s = nullptr;
+    struct HostOut {
+        float states[7 * 256];
+        float quality[8];
+        uint8_t hashes[256];
+    };
+    HostOut *h = reinterpret_cast<HostOut *>(sc.pin);
+    if (cudaMemcpyAsync(d_p, pdqf, 1024, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(d_thr0, &threshold, 4, cudaMemcpyHostToDevice, s) != cudaSuccess)
+        return false;
+    if (launch_dihedrals(d_p, d_thr0, 1, d_hashes, d_quality, nullptr, s) != 0)
+        return false;
+    dihedral_states_kernel<<<1, 256, 0, s>>>(d_p, d_states);
+    g_launches.fetch_add(1);
+    if (cudaMemcpyAsync(h->states, d_states, sizeof h->states, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaMemcpyAsync(h->quality, d_quality, sizeof h->quality, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaMemcpyAsync(h->hashes, d_hashes, sizeof h->hashes, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    // lib.rs:381-419: 7 callbacks; lib.rs:223-224: the callback sees the ORIGINAL threshold
+    HostOut local = *h;  // the callback may re-enter this library on the same thread
+    for (int d = 1; d < 8; d++) {
+        std::memcpy(pdqf, local.states + (d - 1) * 256, 1024);
+        std::memcpy(output, local.hashes + 32 * d, 32);
+        if (!callback(ctx, YUME_PDQ_CUDA_DIHEDRAL_ORDER[d], threshold, local.quality[d]))
+            return false;
+    }
+    return true;
+}
+
+/* ---- (B) ---------------------------------------------------------------- */
+const char *yume_pdq_cuda_error_string(int code)
+{
+    switch (code) {
+    case YUME_PDQ_CUDA_OK: return "ok";
+    case YUME_PDQ_CUDA_E_INVALID: return "invalid argument";
+    case YUME_PDQ_CUDA_E_NO_DEVICE: return "no usable sm_100 CUDA device (there is no CPU fallback)";
+    case YUME_PDQ_CUDA_E_CAPACITY: return "more matches than the output capacity";
+    case YUME_PDQ_CUDA_E_NOMEM: return "out of device or pinned memory";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+int yume_pdq_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char *yume_pdq_cuda_kernel_ident(void) { return "cuda_sm100a_f32_bitexact_scalar_order"; }
+const char *yume_pdq_cuda_matcher_ident(void) { return "CudaMatcher (sm_100a, carry-save prefilter + popc)"; }
+uint64_t yume_pdq_cuda_launch_count(void) { return g_launches.load(); }
+
+int yume_pdq_cuda_hash_batch(int device, const float *frames, size_t n, uint8_t *hashes,
+                             float *quality, float *thresholds, float *pdqf, void *stream)
+{
+    if (!frames || !hashes)
+        return n == 0 ? 0 : YUME_PDQ_CUDA_E_INVALID;
+    if (n == 0)
+        return 0;
+    int rc = ensure_device(device);
+    if (rc)
+        return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool frames_on_host = !is_device_ptr(frames);
+    // outputs: staged through one scratch block when they live on the host
+    Scratch &so = tls_scratch(0);
+    size_t out_need = host_bytes(hashes, n * 256) + host_bytes(quality, n * 32) +
+                      host_bytes(thresholds, n * 32) + host_bytes(pdqf, n * 1024);
+    // frames on the host: double-buffered chunks so the H2D copy of chunk i+1 overlaps
+    // the kernel of chunk i
+    const size_t CH = 64;  // frames per chunk (64 MiB)
+    const size_t chunk = std::min(n, CH);
+    size_t in_need = frames_on_host ? 2 * chunk * (size_t)(512 * 512 * 4) : 0;
+    rc = so.reserve(device, out_need + in_need + 4096, 0);
+    if (rc)
+        return rc;
+    Stager st(s);
+    st.base = reinterpret_cast<uint8_t *>(so.dev);
+    uint8_t *d_hashes;
+    float *d_quality, *d_thr, *d_pdqf;
+    st.out(hashes, n * 256, &d_hashes);
+    st.out(quality, n * 32, &d_quality);
+    st.out(thresholds, n * 32, &d_thr);
+    st.out(pdqf, n * 1024, &d_pdqf);
+    if (!frames_on_host) {
+        rc = launch_hash_batch(frames, n, d_hashes, d_quality, d_thr, d_pdqf, s);
+        if (rc)
+            return rc;
+        return st.finish();
+    }
+    float *d_in[2];
+    d_in[0] = reinterpret_cast<float *>(st.base + align_up(st.off, 256));
+    d_in[1] = d_in[0] + chunk * (512 * 512);
+    static thread_local cudaStream_t copy_stream = nullptr;
+    static thread_local cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    static thread_local int ev_dev = -1;
+    if (ev_dev != device) {
+        YPDQ_CUDA_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            YPDQ_CUDA_TRY(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
+            YPDQ_CUDA_TRY(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
+        }
+        ev_dev = device;
+    }
+    // the copy stream must not start overwriting scratch still in use by earlier work on s
+    YPDQ_CUDA_TRY(cudaEventRecord(ev_done[0], s));
+    YPDQ_CUDA_TRY(cudaStreamWaitEvent(copy_stream, ev_done[0], 0));
+    size_t ci = 0;
+    for (size_t f0 = 0; f0 < n; f0 += chunk, ci++) {
+        const int b = (int)(ci & 1);
+        const size_t cnt = std::min(chunk, n - f0);
+        if (ci >= 2)
+            YPDQ_CUDA_TRY(cudaStreamWaitEvent(copy_stream, ev_done[b], 0));
+        YPDQ_CUDA_TRY(cudaMemcpyAsync(d_in[b], frames + f0 * (512 * 512), cnt * (size_t)(512 * 512 * 4),
+                                      cudaMemcpyHostToDevice, copy_stream));
+        YPDQ_CUDA_TRY(cudaEventRecord(ev_copied[b], copy_stream));
+        YPDQ_CUDA_TRY(cudaStreamWaitEvent(s, ev_copied[b], 0));
+        rc = launch_hash_batch(d_in[b], cnt, d_hashes + f0 * 256, d_quality ? d_quality + f0 * 8 : nullptr,
+                               d_thr ? d_thr + f0 * 8 : nullptr, d_pdqf ? d_pdqf + f0 * 256 : nullptr, s);
+        if (rc)
+            return rc;
+        YPDQ_CUDA_TRY(cudaEventRecord(ev_done[b], s));
+    }
+    rc = st.finish();
+    if (rc)
+        return rc;
+    YPDQ_CUDA_TRY(cudaStreamSynchronize(s));
+    return 0;
+}
+
+#define STAGE_BEGIN(device, total_host_bytes)                                    \
+    int rc = ensure_device(device);                                              \
+    if (rc)                                                                      \
+        return rc;                                                               \
+    cudaStream_t s = (cudaStream_t)stream;                                       \
+    Scratch &so = tls_scratch(0);                                                \
+    rc = so.reserve(device, (total_host_bytes) + 4096, 0);                       \
+    if (rc)                                                                      \
+        return rc;                                                               \
+    Stager st(s);                                                                \
+    st.base = reinterpret_cast<uint8_t *>(so.dev)
+
+int yume_pdq_cuda_jarosz_compress(int device, const float *frames, size_t n, float *buf1, void *stream)
+{
+    if (n == 0)
+        return 0;
+    if (!frames || !buf1)
+        return YUME_PDQ_CUDA_E_INVALID;
+    STAGE_BEGIN(device, host_bytes(frames, n * 1048576) + host_bytes(buf1, n * 65536));
+    const float *d_frames;
+    float *d_buf1;
+    rc = st.in(frames, n * 1048576, &d_frames);
+    if (rc)
+        return rc;
+    st.out(buf1, n * 65536, &d_buf1);
+    rc = launch_jarosz(d_frames, n, d_buf1, s);
+    return rc ? rc : st.finish();
+}
+
+int yume_pdq_cuda_dct2d(int device, const float *buf1, size_t n, float *pdqf, void *stream)
+{
+    if (n == 0)
+        return 0;
+    if (!buf1 || !pdqf)
+        return YUME_PDQ_CUDA_E_INVALID;
+    STAGE_BEGIN(device, host_bytes(buf1, n * 65536) + host_bytes(pdqf, n * 1024));
+    const float *d_buf1;
+    float *d_pdqf;
+    rc = st.in(buf1, n * 65536, &d_buf1);
+    if (rc)
+        return rc;
+    st.out(pdqf, n * 1024, &d_pdqf);
+    rc = launch_dct2d(d_buf1, n, d_pdqf, s);
+    return rc ? rc : st.finish();
+}
+
+int yume_pdq_cuda_sum_of_gradients(int device, const float *pdqf, size_t n, float *gradient,
+                                   float *quality, void *stream)
+{
+    if (n == 0)
+        return 0;
+    if (!pdqf)
+        return YUME_PDQ_CUDA_E_INVALID;
+    STAGE_BEGIN(device, host_bytes(pdqf, n * 1024) + host_bytes(gradient, n * 4) + host_bytes(quality, n * 4));
+    const float *d_pdqf;
+    float *d_g, *d_q;
+    rc = st.in(pdqf, n * 1024, &d_pdqf);
+    if (rc)
+        return rc;
+    st.out(gradient, n * 4, &d_g);
+    st.out(quality, n * 4, &d_q);
+    rc = launch_gradients(d_pdqf, n, d_g, d_q, s);
+    return rc ? rc : st.finish();
+}
+
+int yume_pdq_cuda_quantize(int device, const float *pdqf, size_t n, float *thresholds, uint8_t *hashes,
+                           void *stream)
+{
+    if (n == 0)
+        return 0;
+    if (!pdqf || !thresholds || !hashes)
+        return YUME_PDQ_CUDA_E_INVALID;
+    STAGE_BEGIN(device, host_bytes(pdqf, n * 1024) + host_bytes(thresholds, n * 4) + host_bytes(hashes, n * 32));
+    const float *d_pdqf;
+    float *d_t;
+    uint8_t *d_h;
+    rc = st.in(pdqf, n * 1024, &d_pdqf);
+    if (rc)
+        return rc;
+    st.out(thresholds, n * 4, &d_t);
+    st.out(hashes, n * 32, &d_h);
+    rc = launch_quantize(d_pdqf, n, d_t, d_h, s);
+    return rc ? rc : st.finish();
+}
+
+int yume_pdq_cuda_threshold_2d_f32(int device, const float *pdqf, size_t n, const float *thresholds,
+                                   uint8_t *hashes, void *stream)
+{
+    if (n == 0)
+        return 0;
+    if (!pdqf || !thresholds || !hashes)
+        return YUME_PDQ_CUDA_E_INVALID;
+    STAGE_BEGIN(device, host_bytes(pdqf, n * 1024) + host_bytes(thresholds, n * 4) + host_bytes(hashes, n * 32));
+    const float *d_pdqf, *d_t;
+    uint8_t *d_h;
+    rc = st.in(pdqf, n * 1024, &d_pdqf);
+    if (rc)
+        return rc;
+    rc = st.in(thresholds, n * 4, &d_t);
+    if (rc)
+        return rc;
+    st.out(hashes, n * 32, &d_h);
+    rc = launch_threshold(d_pdqf, n, d_t, d_h, s);
+    return rc ? rc : st.finish();
+}
+
+int yume_pdq_cuda_pdqf_transform(int device, float *pdqf, size_t n, int op, void *stream)
+{
+    if (n == 0)
+        return 0;
+    if (!pdqf || op < 0 || op > YUME_PDQ_CUDA_OP_NEGATE_OFF_DIAGONALS)
+        return YUME_PDQ_CUDA_E_INVALID;
+    STAGE_BEGIN(device, host_bytes(pdqf, n * 1024));
+    float *d_p;
+    if (is_device_ptr(pdqf)) {
+        d_p = pdqf;
+    } else {
+        const float *tmp;
+        rc = st.in((const float *)pdqf, n * 1024, &tmp);
+        if (rc)
+            return rc;
+        d_p = const_cast<float *>(tmp);
+        st.outs.push_back({pdqf, d_p, n * 1024});
+    }
+    rc = launch_transform(d_p, n, op, s);
+    return rc ? rc : st.finish();
+}
+
+int yume_pdq_cuda_dihedrals_batch(int device, const float *pdqf, const float *thr0, size_t n,
+                                  uint8_t *hashes, float *quality, float *thresholds, void *stream)
+{
+    if (n == 0)
+        return 0;
+    if (!pdqf || !thr0 || !hashes)
+        return YUME_PDQ_CUDA_E_INVALID;
+    STAGE_BEGIN(device, host_bytes(pdqf, n * 1024) + host_bytes(thr0, n * 4) + host_bytes(hashes, n * 256) +
+                            host_bytes(quality, n * 32) + host_bytes(thresholds, n * 32));
+    const float *d_pdqf, *d_t0;
+    uint8_t *d_h;
+    float *d_q, *d_t;
+    rc = st.in(pdqf, n * 1024, &d_pdqf);
+    if (rc)
+        return rc;
+    rc = st.in(thr0, n * 4, &d_t0);
+    if (rc)
+        return rc;
+    st.out(hashes, n * 256, &d_h);
+    st.out(quality, n * 32, &d_q);
+    st.out(thresholds, n * 32, &d_t);
+    rc = launch_dihedrals(d_pdqf, d_t0, n, d_h, d_q, d_t, s);
+    return rc ? rc : st.finish();
+}
+
+/* ---- matcher ------------------------------------------------------------ */
+static int db_alloc(int device, size_t n_rows, uint64_t offset, YumePDQ_CudaDb **out)
+{
+    if (!out)
+        return YUME_PDQ_CUDA_E_INVALID;
+    *out = nullptr;
+    int rc = ensure_device(device);
+    if (rc)
+        return rc;
+    YumePDQ_CudaDb *db = new (std::nothrow) YumePDQ_CudaDb();
+    if (!db)
+        return YUME_PDQ_CUDA_E_NOMEM;
+    db->device = device;
+    db->n_rows = n_rows;
+    db->offset = offset;
+    cudaDeviceGetAttribute(&db->sm_count, cudaDevAttrMultiProcessorCount, device);
+    cudaError_t e = cudaMalloc(&db->rows, std::max<size_t>(n_rows * 32, 256));
+    if (e == cudaSuccess)
+        e = cudaMalloc(&db->d_count, 16);
+    if (e == cudaSuccess)
+        e = cudaMallocHost(&db->h_pin, 16);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        yume_pdq_cuda_db_destroy(db);
+        return e == cudaErrorMemoryAllocation ? YUME_PDQ_CUDA_E_NOMEM : (int)e;
+    }
+    db->d_min = reinterpret_cast<unsigned long long *>(db->d_count + 2);
+    *out = db;
+    return 0;
+}
+
+int yume_pdq_cuda_db_create(int device, const uint8_t *rows, size_t n_rows, uint64_t global_row_offset,
+                            YumePDQ_CudaDb **out)
+{
+    if (n_rows && !rows)
+        return YUME_PDQ_CUDA_E_INVALID;
+    int rc = db_alloc(device, n_rows, global_row_offset, out);
+    if (rc)
+        return rc;
+    if (n_rows) {
+        cudaError_t e = cudaMemcpy((*out)->rows, rows, n_rows * 32, cudaMemcpyDefault);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            yume_pdq_cuda_db_destroy(*out);
+            *out = nullptr;
+            return (int)e;
+        }
+    }
+    return 0;
+}
+
+int yume_pdq_cuda_db_create_synthetic(int device, size_t n_rows, uint64_t global_row_offset, uint64_t seed,
+                                      YumePDQ_CudaDb **out)
+{
+    int rc = db_alloc(device, n_rows, global_row_offset, out);
+    if (rc)
+        return rc;
+    rc = launch_synth_rows((*out)->rows, n_rows, global_row_offset, seed, nullptr);
+    if (rc == 0) {
+        cudaError_t e = cudaDeviceSynchronize();
+        rc = e == cudaSuccess ? 0 : (int)e;
+    }
+    if (rc) {
+        yume_pdq_cuda_db_destroy(*out);
+        *out = nullptr;
+    }
+    return rc;
+}
+
+int yume_pdq_cuda_db_destroy(YumePDQ_CudaDb *db)
+{
+    if (!db)
+        return 0;
+    cudaSetDevice(db->device);
+    if (db->rows) cudaFree(db->rows);
+    if (db->d_needles) cudaFree(db->d_needles);
+    if (db->d_out) cudaFree(db->d_out);
+    if (db->d_count) cudaFree(db->d_count);
+    if (db->h_pin) cudaFreeHost(db->h_pin);
+    (void)cudaGetLastError();
+    delete db;
+    return 0;
+}
+
+size_t yume_pdq_cuda_db_len(const YumePDQ_CudaDb *db) { return db ? db->n_rows : 0; }
+int yume_pdq_cuda_db_device(const YumePDQ_CudaDb *db) { return db ? db->device : -1; }
+const uint8_t *yume_pdq_cuda_db_rows(const YumePDQ_CudaDb *db) { return db ? db->rows : nullptr; }
+
+int yume_pdq_cuda_db_write_rows(YumePDQ_CudaDb *db, size_t first, const uint8_t *rows, size_t n)
+{
+    if (!db || (n && !rows) || first > db->n_rows || n > db->n_rows - first)
+        return YUME_PDQ_CUDA_E_INVALID;
+    int rc = ensure_device(db->device);
+    if (rc)
+        return rc;
+    if (n)
+        YPDQ_CUDA_TRY(cudaMemcpy(db->rows + first * 32, rows, n * 32, cudaMemcpyDefault));
+    return 0;
+}
+
+// shared host-facing driver: mode LIST (hits copied back + sorted) or MIN
+static int match_host(YumePDQ_CudaDb *db, const uint8_t *needles, size_t q, uint32_t threshold, int mode,
+                      std::vector<YumePDQ_Match> *hits, size_t want, size_t *total,
+                      unsigned long long *min_key, cudaStream_t s)
+{
+    if (!db || !needles || q == 0 || q > 0xffffffffull)
+        return YUME_PDQ_CUDA_E_INVALID;
+    int rc = ensure_device(db->device);
+    if (rc)
+        return rc;
+    std::lock_guard<std::mutex> lock(db->mu);
+    const uint8_t *d_needles = needles;
+    if (!is_device_ptr(needles)) {
+        if (db->needles_cap < q * 32) {
+            if (db->d_needles) cudaFree(db->d_needles);
+            db->d_needles = nullptr;
+            db->needles_cap = 0;
+            YPDQ_CUDA_TRY(cudaMalloc(&db->d_needles, align_up(q * 32, 4096)));
+            db->needles_cap = align_up(q * 32, 4096);
+        }
+        YPDQ_CUDA_TRY(cudaMemcpyAsync(db->d_needles, needles, q * 32, cudaMemcpyHostToDevice, s));
+        d_needles = db->d_needles;
+    }
+    size_t cap = mode == MODE_LIST ? std::max<size_t>(want, 1024) : 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (mode == MODE_LIST && db->out_cap < cap) {
+            if (db->d_out) cudaFree(db->d_out);
+            db->d_out = nullptr;
+            db->out_cap = 0;
+            cudaError_t e = cudaMalloc(&db->d_out, cap * sizeof(YumePDQ_Match));
+            if (e != cudaSuccess) {
+                (void)cudaGetLastError();
+                return YUME_PDQ_CUDA_E_NOMEM;
+            }
+            db->out_cap = cap;
+        }
+        const uint32_t dev_cap = (uint32_t)std::min<size_t>(db->out_cap, 0xffffffffu);
+        struct Init {
+            uint32_t count, pad;
+            unsigned long long min;
+        } init = {0, 0, ~0ull};
+        std::memcpy(db->h_pin, &init, 16);
+        YPDQ_CUDA_TRY(cudaMemcpyAsync(db->d_count, db->h_pin, 16, cudaMemcpyHostToDevice, s));
+        rc = launch_match(db->rows, db->n_rows, db->offset, d_needles, q, threshold, db->d_out,
+                          mode == MODE_LIST ? dev_cap : 0, db->d_count, db->d_min, mode,
+                          YUME_PDQ_CUDA_ALGO_AUTO, db->sm_count, s);
+        if (rc)
+            return rc;
+        YPDQ_CUDA_TRY(cudaMemcpyAsync(db->h_pin, db->d_count, 16, cudaMemcpyDeviceToHost, s));
+        YPDQ_CUDA_TRY(cudaStreamSynchronize(s));
+        Init res;
+        std::memcpy(&res, db->h_pin, 16);
+        *total = res.count;
+        if (min_key)
+            *min_key = res.min;
+        if (mode != MODE_LIST)
+            return 0;
+        if (res.count > dev_cap) {  // rare: grow the device list and rescan so the sorted prefix is exact
+            cap = res.count;
+            continue;
+        }
+        hits->resize(res.count);
+        if (res.count)
+            YPDQ_CUDA_TRY(cudaMemcpy(hits->data(), db->d_out, res.count * sizeof(YumePDQ_Match),
+                                     cudaMemcpyDeviceToHost));
+        std::sort(hits->begin(), hits->end(), [](const YumePDQ_Match &a, const YumePDQ_Match &b) {
+            return a.row != b.row ? a.row < b.row : a.needle < b.needle;
+        });
+        return 0;
+    }
+    return YUME_PDQ_CUDA_E_CAPACITY;
+}
+
+int yume_pdq_cuda_matcher_scan(YumePDQ_CudaDb *db, const uint8_t *needles, size_t q, uint32_t threshold,
+                               int *matched, void *stream)
+{
+    if (!matched)
+        return YUME_PDQ_CUDA_E_INVALID;
+    size_t total = 0;
+    unsigned long long mk;
+    int rc = match_host(db, needles, q, threshold, MODE_MIN, nullptr, 0, &total, &mk, (cudaStream_t)stream);
+    if (rc)
+        return rc;
+    *matched = total != 0;
+    return 0;
+}
+
+int yume_pdq_cuda_matcher_find(YumePDQ_CudaDb *db, const uint8_t *needles, size_t q, uint32_t threshold,
+                               YumePDQ_Match *out, size_t cap, size_t *n_found, void *stream)
+{
+    if (!n_found || (cap && !out))
+        return YUME_PDQ_CUDA_E_INVALID;
+    std::vector<YumePDQ_Match> hits;
+    size_t total = 0;
+    int rc = match_host(db, needles, q, threshold, MODE_LIST, &hits, cap, &total, nullptr,
+                        (cudaStream_t)stream);
+    if (rc)
+        return rc;
+    *n_found = total;
+    const size_t k = std::min(cap, hits.size());
+    if (k)
+        std::memcpy(out, hits.data(), k * sizeof(YumePDQ_Match));
+    return total > cap ? YUME_PDQ_CUDA_E_CAPACITY : 0;
+}
+
+int yume_pdq_cuda_matcher_find_min(YumePDQ_CudaDb *db, const uint8_t *needles, size_t q, uint32_t threshold,
+                                   uint64_t *min_key, void *stream)
+{
+    if (!min_key)
+        return YUME_PDQ_CUDA_E_INVALID;
+    size_t total = 0;
+    unsigned long long mk = ~0ull;
+    int rc = match_host(db, needles, q, threshold, MODE_MIN, nullptr, 0, &total, &mk, (cudaStream_t)stream);
+    if (rc)
+        return rc;
+    *min_key = total ? (uint64_t)mk : UINT64_MAX;
+    return 0;
+}
+
+int yume_pdq_cuda_matcher_find_device(YumePDQ_CudaDb *db, const uint8_t *needles_dev, size_t q,
+                                      uint32_t threshold, YumePDQ_Match *out_dev, uint32_t cap,
+                                      uint32_t *count_dev, int algo, void *stream)
+{
+    if (!db || !needles_dev || !count_dev || q == 0 || (cap && !out_dev))
+        return YUME_PDQ_CUDA_E_INVALID;
+    int rc = ensure_device(db->device);
+    if (rc)
+        return rc;
+    return launch_match(db->rows, db->n_rows, db->offset, needles_dev, q, threshold, out_dev, cap,
+                        count_dev, nullptr, MODE_LIST, algo, db->sm_count, (cudaStream_t)stream);
+}
+
+int yume_pdq_cuda_synth_frames(int device, float *frames_dev, size_t n, uint64_t first_frame, uint64_t seed,
+                               int kind, void *stream)
+{
+    if (n && !frames_dev)
+        return YUME_PDQ_CUDA_E_INVALID;
+    int rc = ensure_device(device);
+    if (rc)
+        return rc;
+    return launch_synth_frames(frames_dev, n, first_frame, seed, kind, (cudaStream_t)stream);
+}
+
+int yume_pdq_cuda_synth_rows(int device, uint8_t *rows_dev, size_t n_rows, uint64_t first_row, uint64_t seed,
+                             void *stream)
+{
+    if (n_rows && !rows_dev)
+        return YUME_PDQ_CUDA_E_INVALID;
+    int rc = ensure_device(device);
+    if (rc)
+        return rc;
+    return launch_synth_rows(rows_dev, n_rows, first_row, seed, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,68 @@
+// common.cuh -- shared helpers for the sm_100a kernels and the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/yume_pdq_cuda.h"
+
+namespace ypdq {
+
+extern std::atomic<uint64_t> g_launches;  // counted at every kernel launch (api.cu)
+
+#define YPDQ_CUDA_TRY(expr)                                  \
+    do {                                                     \
+        cudaError_t _e = (expr);                             \
+        if (_e != cudaSuccess) {                             \
+            (void)cudaGetLastError();                        \
+            return (int)_e;                                  \
+        }                                                    \
+    } while (0)
+
+#define YPDQ_LAUNCH_CHECK()                                  \
+    do {                                                     \
+        ::ypdq::g_launches.fetch_add(1, std::memory_order_relaxed); \
+        cudaError_t _e = cudaGetLastError();                 \
+        if (_e != cudaSuccess)                               \
+            return (int)_e;                                  \
+    } while (0)
+
+// true if `p` is memory the device can address directly on `device`
+inline bool is_device_ptr(const void *p)
+{
+    if (!p)
+        return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int ensure_device(int device);  // api.cu: validates + cudaSetDevice, returns 0 or error
+
+// ---- kernel launchers (defined in hasher.cu / matcher.cu / synth.cu) ----
+int launch_hash_batch(const float *frames, size_t n, uint8_t *hashes, float *quality,
+                      float *thresholds, float *pdqf, cudaStream_t s);
+int launch_jarosz(const float *frames, size_t n, float *buf1, cudaStream_t s);
+int launch_dct2d(const float *buf1, size_t n, float *pdqf, cudaStream_t s);
+int launch_gradients(const float *pdqf, size_t n, float *gradient, float *quality, cudaStream_t s);
+int launch_quantize(const float *pdqf, size_t n, float *thresholds, uint8_t *hashes, cudaStream_t s);
+int launch_threshold(const float *pdqf, size_t n, const float *thresholds, uint8_t *hashes,
+                     cudaStream_t s);
+int launch_transform(float *pdqf, size_t n, int op, cudaStream_t s);
+int launch_dihedrals(const float *pdqf, const float *thr0, size_t n, uint8_t *hashes, float *quality,
+                     float *thresholds, cudaStream_t s);
+
+enum MatchMode : int { MODE_LIST = 0, MODE_MIN = 1 };
+int launch_match(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
+                 size_t q, uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
+                 unsigned long long *min_key, int mode, int algo, int sm_count, cudaStream_t s);
+
+int launch_synth_frames(float *frames, size_t n, uint64_t first, uint64_t seed, int kind,
+                        cudaStream_t s);
+int launch_synth_rows(uint8_t *rows, size_t n, uint64_t first, uint64_t seed, cudaStream_t s);
+
+}  // namespace ypdq

@@ -1,0 +1,556 @@
+// hasher.cu -- batched PDQ-variant hasher for sm_100a.
+//
+// One CTA of 128 threads hashes one 512x512 f32 frame in a single pass over the
+// frame and emits all 8 dihedral hashes.  It reproduces the reference scalar
+// kernel (DefaultKernel, /root/reference src/kernel/mod.rs) BIT FOR BIT:
+//   jarosz_compress   mod.rs:644-666   tent 7x7 (5x5 effective), di outer / dj inner,
+//                                      separate f32 multiply and add (no FMA)
+//   dct2d             mod.rs:543-574   D(16x127) B D^T with 4 round-robin partial
+//                                      sums per dot product, ((s0+s1)+s2)+s3
+//   sum_of_gradients  mod.rs:617-642   sequential f32 accumulation
+//   quantize          mod.rs:595-608   Torben lower median sorted[127], bit = v > median
+//   visit_dihedrals   lib.rs:358-420   sign flips / transpose in frequency space
+//                                      (even-row convention of x86.rs:285-326)
+// so __fmul_rn/__fadd_rn are used everywhere a rounding happens (never
+// contracted to FMA) and the summation orders are the reference's.
+//
+// Mapping: thread j owns output column j of the 127x127 tent image.
+// For every tent row oi it loads its 5x5 window straight from global memory with
+// 128-bit loads (a warp reads 512 contiguous bytes per instruction; the row
+// shared between consecutive windows stays in registers), produces B[oi][j] and
+// immediately applies the rank-1 update T[k][j] += D[k][oi] * B[oi][j] for the 16
+// DCT rows -- 64 accumulators (16 k x 4 partial sums) in registers, so the
+// 127x127 intermediate never exists in memory.  No synchronisation happens while
+// the frame streams; one lane prefetches the rows 8 windows ahead into L2
+// (cp.async.bulk.prefetch.L2).  The two ~1e-40 residue weights of the reference
+// LUT (TENT[0][4], TENT[0][5]) are not applied: they cannot change any result
+// unless a whole 5x5 window is exactly zero (documented in DESIGN.md).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+#include "../../include/yume_pdq_luts.h"
+#include "common.cuh"
+
+namespace ypdq {
+
+namespace {
+
+constexpr int HT = 128;          // threads per CTA
+constexpr int TSTRIDE = 129;     // padded row stride of the 16x127 stage-1 result
+constexpr int PREFETCH_AHEAD = 8;
+
+__device__ __align__(16) float g_dt[127 * 16];          // D transposed, g_dt[k2*16 + k] = D[k][k2]
+__constant__ uint32_t c_tent_bits[49];    // W[di][dj], read as constant-bank operands
+
+struct __align__(16) HashSmem {
+    float dt[127 * 16];        // D transposed: dt[k2*16 + k] = D[k][k2]
+    float t[16 * TSTRIDE];     // stage-1 result T[k][j]
+    float p[256];              // PDQF
+    float thr[4];              // medians of P, C.P, R.C.P, R.P
+};
+
+__device__ __forceinline__ float4 ldg4(const float *p)
+{
+    return __ldg(reinterpret_cast<const float4 *>(p));
+}
+
+__device__ __forceinline__ void prefetch_l2(const void *p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// weight W[di][dj] of the tent LUT as a compile-time-indexed constant load
+__device__ __forceinline__ float tent_w(int di, int dj)
+{
+    return __uint_as_float(c_tent_bits[di * 7 + dj]);
+}
+
+// ---- window row DI (1..5): five taps in reference order (dj = 1..5); a = columns
+// 4j..4j+3, b = columns 4j+4..4j+7, the window is columns 4j+2..4j+6 ----
+template <int DI>
+__device__ __forceinline__ float tent_row(float sum, const float4 &a, const float4 &b)
+{
+    sum = __fadd_rn(sum, __fmul_rn(tent_w(DI, 1), a.z));
+    sum = __fadd_rn(sum, __fmul_rn(tent_w(DI, 2), a.w));
+    sum = __fadd_rn(sum, __fmul_rn(tent_w(DI, 3), b.x));
+    sum = __fadd_rn(sum, __fmul_rn(tent_w(DI, 4), b.y));
+    sum = __fadd_rn(sum, __fmul_rn(tent_w(DI, 5), b.z));
+    return sum;
+}
+
+// value of dihedral d's PDQF at (i, j), from the untransformed PDQF in shared memory.
+// d: 0 P, 1 C.P, 2 R.C.P, 3 R.P, 4 P^T, 5 R.P^T, 6 C.R.P^T, 7 C.P^T with
+// C = negate even columns (pdqf_negate_alt_cols::<false>, mod.rs:368-382) and
+// R = negate even rows (pdqf_negate_alt_rows::<true>, x86.rs:285-326).
+__device__ __forceinline__ float dihedral_value(const float *p, int d, int i, int j)
+{
+    float v = (d & 4) ? p[j * 16 + i] : p[i * 16 + j];
+    const bool c = (0xC6 >> d) & 1;  // d in {1,2,6,7}
+    const bool r = (0x6C >> d) & 1;  // d in {2,3,5,6}
+    const bool neg = (c && !(j & 1)) != (r && !(i & 1));
+    return neg ? -v : v;
+}
+
+// order-preserving map f32 -> u32 (for the radix select)
+__device__ __forceinline__ uint32_t f2key(float f)
+{
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// Lower median sorted[127] of the 256 values of sign-variant `variant` (0 P, 1 C.P,
+// 2 R.C.P, 3 R.P): what torben_median (mod.rs:212-253) returns.  One warp, MSB-first
+// radix select over order-preserving keys; 8 values per lane.
+__device__ float warp_lower_median(const float *p, int variant, int lane)
+{
+    uint32_t key[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        int idx = lane + 32 * e;
+        key[e] = f2key(dihedral_value(p, variant, idx >> 4, idx & 15));
+    }
+    uint32_t alive = 0xffu, prefix = 0, k = 127;
+    for (int bit = 31; bit >= 0; bit--) {
+        uint32_t zeros = 0;
+#pragma unroll
+        for (int e = 0; e < 8; e++)
+            zeros |= (((key[e] >> bit) & 1u) ^ 1u) << e;
+        uint32_t cnt0 = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(alive & zeros));
+        if (k < cnt0) {
+            alive &= zeros;
+        } else {
+            k -= cnt0;
+            alive &= ~zeros;
+            prefix |= 1u << bit;
+        }
+    }
+    return key2f(prefix);
+}
+
+// sum_of_gradients (mod.rs:617-642) of dihedral d, sequential like the reference
+__device__ float gradient_sum(const float *p, int d)
+{
+    float g = 0.0f;
+    for (int i = 0; i < 15; i++)
+        for (int j = 0; j < 16; j++)
+            g = __fadd_rn(g, fabsf(__fsub_rn(dihedral_value(p, d, i, j), dihedral_value(p, d, i + 1, j))));
+    for (int i = 0; i < 16; i++)
+        for (int j = 0; j < 15; j++)
+            g = __fadd_rn(g, fabsf(__fsub_rn(dihedral_value(p, d, i, j), dihedral_value(p, d, i, j + 1))));
+    return g;
+}
+
+__device__ __forceinline__ float adjust_quality(float g)
+{
+    float s = __fdiv_rn(g, 180.0f);  // QUALITY_ADJUST_DIVISOR, mod.rs:257
+    return s < 1.0f ? s : 1.0f;      // f32::min(scaled, 1.0): NaN -> 1.0
+}
+
+// 256 hash bits of dihedral d against threshold thr; all 128 threads participate.
+// Flat index i = 16*row + col -> byte 31 - i/8, bit i%8 (mod.rs:595-608, threshold.rs:37-119).
+__device__ __forceinline__ void write_hash_bits(const float *p, int d, float thr, uint8_t *out,
+                                                int tid)
+{
+    uint32_t *out32 = reinterpret_cast<uint32_t *>(out);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        int idx = tid + 128 * h;  // warp w covers ballot word b = w + 4h
+        bool bit = dihedral_value(p, d, idx >> 4, idx & 15) > thr;
+        uint32_t b = __ballot_sync(0xffffffffu, bit);
+        if ((tid & 31) == 0) {
+            int word = (tid >> 5) + 4 * h;                 // indices 32*word .. 32*word+31
+            out32[7 - word] = __byte_perm(b, 0, 0x0123);   // byte 31-4*word holds bits 0..7
+        }
+    }
+}
+
+// Epilogue shared by the fused kernel and the per-stage entry points: from the PDQF in
+// sm.p compute medians, 8 hashes, 8 qualities, 8 thresholds.
+__device__ void dihedral_epilogue(HashSmem &sm, int tid, uint8_t *hashes, float *quality,
+                                  float *thresholds, bool have_thr0, float thr0)
+{
+    const int warp = tid >> 5, lane = tid & 31;
+    // visit_dihedrals (lib.rs:358-420): thr0 is the caller's threshold for NORMAL; the three
+    // sign variants get a fresh quantize
+    float med = 0.0f;
+    if (!(have_thr0 && warp == 0))
+        med = warp_lower_median(sm.p, warp, lane);
+    if (lane == 0)
+        sm.thr[warp] = (have_thr0 && warp == 0) ? thr0 : med;
+    __syncthreads();
+#pragma unroll 1
+    for (int d = 0; d < 8; d++)
+        write_hash_bits(sm.p, d, sm.thr[d & 3], hashes + 32 * d, tid);
+    if (tid < 8) {
+        if (thresholds)
+            thresholds[tid] = sm.thr[tid & 3];
+        if (quality)
+            quality[tid] = adjust_quality(gradient_sum(sm.p, tid));
+    }
+}
+
+__device__ __forceinline__ void load_dt(HashSmem &sm, int tid)
+{
+    const float4 *src = reinterpret_cast<const float4 *>(g_dt);
+    float4 *dst = reinterpret_cast<float4 *>(sm.dt);
+    for (int i = tid; i < 127 * 4; i += HT)
+        dst[i] = src[i];
+}
+
+// stage 2 of dct2d (mod.rs:563-570): PDQF[k][jj] = sum_m T[k][m] * D[jj][m], 4 partial sums
+__device__ __forceinline__ void dct_stage2(HashSmem &sm, int tid)
+{
+    const int k = tid >> 3, jj = (tid & 7) * 2;
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+    const float *trow = sm.t + k * TSTRIDE;
+#pragma unroll 4
+    for (int m = 0; m < 124; m += 4) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            float tv = trow[m + r];
+            float2 dv = *reinterpret_cast<const float2 *>(&sm.dt[(m + r) * 16 + jj]);
+            s0[r] = __fadd_rn(s0[r], __fmul_rn(tv, dv.x));
+            s1[r] = __fadd_rn(s1[r], __fmul_rn(tv, dv.y));
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+        float tv = trow[124 + r];
+        float2 dv = *reinterpret_cast<const float2 *>(&sm.dt[(124 + r) * 16 + jj]);
+        s0[r] = __fadd_rn(s0[r], __fmul_rn(tv, dv.x));
+        s1[r] = __fadd_rn(s1[r], __fmul_rn(tv, dv.y));
+    }
+    sm.p[k * 16 + jj] = __fadd_rn(__fadd_rn(__fadd_rn(s0[0], s0[1]), s0[2]), s0[3]);
+    sm.p[k * 16 + jj + 1] = __fadd_rn(__fadd_rn(__fadd_rn(s1[0], s1[1]), s1[2]), s1[3]);
+}
+
+// rank-1 update of the 16x4 accumulators with tent value b of row k2 (k2 & 3 == R)
+template <int R>
+__device__ __forceinline__ void rank1(float (&acc)[16][4], const float *dt_row, float b)
+{
+#pragma unroll
+    for (int kq = 0; kq < 4; kq++) {
+        const float4 d = *reinterpret_cast<const float4 *>(dt_row + 4 * kq);
+        acc[4 * kq + 0][R] = __fadd_rn(acc[4 * kq + 0][R], __fmul_rn(d.x, b));
+        acc[4 * kq + 1][R] = __fadd_rn(acc[4 * kq + 1][R], __fmul_rn(d.y, b));
+        acc[4 * kq + 2][R] = __fadd_rn(acc[4 * kq + 2][R], __fmul_rn(d.z, b));
+        acc[4 * kq + 3][R] = __fadd_rn(acc[4 * kq + 3][R], __fmul_rn(d.w, b));
+    }
+}
+
+// ------------------------------------------------------------ fused kernel --
+__global__ void __launch_bounds__(HT, 4)
+hash_fused_kernel(const float *__restrict__ frames, size_t n, uint8_t *__restrict__ hashes,
+                  float *__restrict__ quality, float *__restrict__ thresholds,
+                  float *__restrict__ pdqf_out)
+{
+    __shared__ HashSmem sm;
+    const int tid = threadIdx.x;
+    const int j = tid < 127 ? tid : 126;  // thread 127 shadows column 126 (never stored)
+    load_dt(sm, tid);
+    __syncthreads();
+
+    for (size_t f = blockIdx.x; f < n; f += gridDim.x) {
+        const float *frame = frames + f * (512 * 512);
+        // window of output (oi, j): rows 4oi+2 .. 4oi+6, columns 4j+2 .. 4j+6
+        const float *col = frame + 4 * j;
+        if (tid == 0) {
+#pragma unroll 1
+            for (int a = 0; a < PREFETCH_AHEAD; a++)
+                prefetch_l2(frame + (size_t)(4 * a + 2) * 512, 4 * 2048);
+        }
+        float acc[16][4];
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                acc[k][r] = 0.0f;
+
+        // first window row (input row 2), carried between iterations afterwards
+        float4 ca = ldg4(col + 2 * 512), cb = ldg4(col + 2 * 512 + 4);
+
+        auto one_row = [&](int oi, auto rtag) {
+            constexpr int R = decltype(rtag)::value;  // oi & 3
+            const float *base = col + (size_t)(4 * oi + 3) * 512;
+            float4 a1 = ldg4(base), b1 = ldg4(base + 4);
+            float4 a2 = ldg4(base + 512), b2 = ldg4(base + 512 + 4);
+            float4 a3 = ldg4(base + 1024), b3 = ldg4(base + 1024 + 4);
+            float4 a4 = ldg4(base + 1536), b4 = ldg4(base + 1536 + 4);
+            if (tid == 0 && oi + PREFETCH_AHEAD < 127)
+                prefetch_l2(frame + (size_t)(4 * (oi + PREFETCH_AHEAD) + 3) * 512, 4 * 2048);
+            float sum = 0.0f;
+            sum = tent_row<1>(sum, ca, cb);
+            sum = tent_row<2>(sum, a1, b1);
+            sum = tent_row<3>(sum, a2, b2);
+            sum = tent_row<4>(sum, a3, b3);
+            sum = tent_row<5>(sum, a4, b4);
+            ca = a4;
+            cb = b4;
+            rank1<R>(acc, sm.dt + oi * 16, sum);
+        };
+        using T0 = std::integral_constant<int, 0>;
+        using T1 = std::integral_constant<int, 1>;
+        using T2 = std::integral_constant<int, 2>;
+        using T3 = std::integral_constant<int, 3>;
+#pragma unroll 1
+        for (int oi = 0; oi < 124; oi += 4) {
+            one_row(oi, T0{});
+            one_row(oi + 1, T1{});
+            one_row(oi + 2, T2{});
+            one_row(oi + 3, T3{});
+        }
+        one_row(124, T0{});
+        one_row(125, T1{});
+        one_row(126, T2{});
+
+        __syncthreads();  // previous frame's epilogue has finished with sm.t / sm.p
+        if (tid < 127) {
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                sm.t[k * TSTRIDE + tid] =
+                    __fadd_rn(__fadd_rn(__fadd_rn(acc[k][0], acc[k][1]), acc[k][2]), acc[k][3]);
+        }
+        __syncthreads();
+        dct_stage2(sm, tid);
+        __syncthreads();
+        if (pdqf_out) {
+            pdqf_out[f * 256 + tid] = sm.p[tid];
+            pdqf_out[f * 256 + 128 + tid] = sm.p[128 + tid];
+        }
+        dihedral_epilogue(sm, tid, hashes + f * 256, quality ? quality + f * 8 : nullptr,
+                          thresholds ? thresholds + f * 8 : nullptr, false, 0.0f);
+    }
+}
+
+// ------------------------------------------------- per-stage (Kernel trait) --
+// Kernel::jarosz_compress: one thread per output pixel, same arithmetic as above.
+__global__ void __launch_bounds__(128)
+jarosz_kernel(const float *__restrict__ frames, float *__restrict__ buf1)
+{
+    const size_t f = blockIdx.y;
+    const int oi = blockIdx.x, oj = threadIdx.x;  // grid.x = 128 rows, 128 threads
+    float *out = buf1 + f * (128 * 128) + oi * 128 + oj;
+    if (oi >= 127 || oj >= 127) {
+        *out = 0.0f;  // zero padding of the 128x128 buffer (x86.rs:756-757, lib.rs:296-297)
+        return;
+    }
+    const float *base = frames + f * (512 * 512) + (size_t)(4 * oi + 2) * 512 + 4 * oj;
+    float sum = 0.0f;
+    sum = tent_row<1>(sum, ldg4(base), ldg4(base + 4));
+    sum = tent_row<2>(sum, ldg4(base + 512), ldg4(base + 512 + 4));
+    sum = tent_row<3>(sum, ldg4(base + 1024), ldg4(base + 1024 + 4));
+    sum = tent_row<4>(sum, ldg4(base + 1536), ldg4(base + 1536 + 4));
+    sum = tent_row<5>(sum, ldg4(base + 2048), ldg4(base + 2048 + 4));
+    *out = sum;
+}
+
+// Kernel::dct2d on a 128x128 (127x127 valid) buffer
+__global__ void __launch_bounds__(HT)
+dct2d_kernel(const float *__restrict__ buf1, float *__restrict__ pdqf)
+{
+    __shared__ HashSmem sm;
+    const int tid = threadIdx.x;
+    const int j = tid < 127 ? tid : 126;
+    load_dt(sm, tid);
+    __syncthreads();
+    const float *b = buf1 + (size_t)blockIdx.x * (128 * 128) + j;
+    float acc[16][4];
+#pragma unroll
+    for (int k = 0; k < 16; k++)
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+            acc[k][r] = 0.0f;
+#pragma unroll 1
+    for (int k2 = 0; k2 < 124; k2 += 4) {
+        rank1<0>(acc, sm.dt + (k2 + 0) * 16, __ldg(b + (k2 + 0) * 128));
+        rank1<1>(acc, sm.dt + (k2 + 1) * 16, __ldg(b + (k2 + 1) * 128));
+        rank1<2>(acc, sm.dt + (k2 + 2) * 16, __ldg(b + (k2 + 2) * 128));
+        rank1<3>(acc, sm.dt + (k2 + 3) * 16, __ldg(b + (k2 + 3) * 128));
+    }
+    rank1<0>(acc, sm.dt + 124 * 16, __ldg(b + 124 * 128));
+    rank1<1>(acc, sm.dt + 125 * 16, __ldg(b + 125 * 128));
+    rank1<2>(acc, sm.dt + 126 * 16, __ldg(b + 126 * 128));
+    if (tid < 127) {
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            sm.t[k * TSTRIDE + tid] =
+                __fadd_rn(__fadd_rn(__fadd_rn(acc[k][0], acc[k][1]), acc[k][2]), acc[k][3]);
+    }
+    __syncthreads();
+    dct_stage2(sm, tid);
+    __syncthreads();
+    pdqf[(size_t)blockIdx.x * 256 + tid] = sm.p[tid];
+    pdqf[(size_t)blockIdx.x * 256 + 128 + tid] = sm.p[128 + tid];
+}
+
+// what: 0 gradients(+quality), 1 quantize, 2 threshold_2d_f32, 3 dihedrals
+__global__ void __launch_bounds__(HT)
+pdqf_ops_kernel(const float *__restrict__ pdqf, int what, const float *__restrict__ thr_in,
+                float *__restrict__ f_out0, float *__restrict__ f_out1,
+                uint8_t *__restrict__ hashes)
+{
+    __shared__ HashSmem sm;
+    const int tid = threadIdx.x;
+    const size_t f = blockIdx.x;
+    sm.p[tid] = pdqf[f * 256 + tid];
+    sm.p[128 + tid] = pdqf[f * 256 + 128 + tid];
+    __syncthreads();
+    if (what == 0) {
+        if (tid == 0) {
+            float g = gradient_sum(sm.p, 0);
+            if (f_out0)
+                f_out0[f] = g;
+            if (f_out1)
+                f_out1[f] = adjust_quality(g);
+        }
+    } else if (what == 1) {
+        if (tid < 32) {
+            float med = warp_lower_median(sm.p, 0, tid);
+            if (tid == 0) {
+                sm.thr[0] = med;
+                f_out0[f] = med;
+            }
+        }
+        __syncthreads();
+        write_hash_bits(sm.p, 0, sm.thr[0], hashes + f * 32, tid);
+    } else if (what == 2) {
+        write_hash_bits(sm.p, 0, thr_in[f], hashes + f * 32, tid);
+    } else {
+        dihedral_epilogue(sm, tid, hashes + f * 256, f_out0 ? f_out0 + f * 8 : nullptr,
+                          f_out1 ? f_out1 + f * 8 : nullptr, true, thr_in[f]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pdqf_transform_kernel(float *__restrict__ pdqf, int op)
+{
+    __shared__ float p[256];
+    const int tid = threadIdx.x, i = tid >> 4, j = tid & 15;
+    float *base = pdqf + (size_t)blockIdx.x * 256;
+    p[tid] = base[tid];
+    __syncthreads();
+    float v = p[tid];
+    switch (op) {
+    case YUME_PDQ_CUDA_OP_T: v = p[j * 16 + i]; break;
+    case YUME_PDQ_CUDA_OP_NEGATE_ALT_COLS_FALSE: if (!(j & 1)) v = -v; break;
+    case YUME_PDQ_CUDA_OP_NEGATE_ALT_COLS_TRUE: if (j & 1) v = -v; break;
+    case YUME_PDQ_CUDA_OP_NEGATE_ALT_ROWS_TRUE: if (!(i & 1)) v = -v; break;
+    case YUME_PDQ_CUDA_OP_NEGATE_ALT_ROWS_FALSE: if (i & 1) v = -v; break;
+    case YUME_PDQ_CUDA_OP_NEGATE_OFF_DIAGONALS: if ((j - i) & 1) v = -v; break;
+    default: break;
+    }
+    base[tid] = v;
+}
+
+int upload_luts()
+{
+    static thread_local int done_dev = -1;
+    int dev = 0;
+    YPDQ_CUDA_TRY(cudaGetDevice(&dev));
+    if (done_dev == dev)
+        return 0;
+    static uint32_t dt[127 * 16];
+    for (int k = 0; k < 16; k++)
+        for (int k2 = 0; k2 < 127; k2++)
+            dt[k2 * 16 + k] = YUME_PDQ_DCT_MATRIX_BITS[k * 127 + k2];
+    YPDQ_CUDA_TRY(cudaMemcpyToSymbol(g_dt, dt, sizeof dt));
+    YPDQ_CUDA_TRY(cudaMemcpyToSymbol(c_tent_bits, YUME_PDQ_TENT_WEIGHT_BITS, sizeof(uint32_t) * 49));
+    done_dev = dev;
+    return 0;
+}
+
+}  // namespace
+
+int launch_hash_batch(const float *frames, size_t n, uint8_t *hashes, float *quality,
+                      float *thresholds, float *pdqf, cudaStream_t s)
+{
+    if (n == 0)
+        return 0;
+    int rc = upload_luts();
+    if (rc)
+        return rc;
+    unsigned grid = (unsigned)std::min<size_t>(n, (size_t)1 << 30);
+    hash_fused_kernel<<<grid, HT, 0, s>>>(frames, n, hashes, quality, thresholds, pdqf);
+    YPDQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_jarosz(const float *frames, size_t n, float *buf1, cudaStream_t s)
+{
+    int rc = upload_luts();
+    if (rc)
+        return rc;
+    for (size_t f0 = 0; f0 < n; f0 += 65535) {
+        unsigned cnt = (unsigned)std::min<size_t>(65535, n - f0);
+        jarosz_kernel<<<dim3(128, cnt), 128, 0, s>>>(frames + f0 * 512 * 512, buf1 + f0 * 128 * 128);
+        YPDQ_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int launch_dct2d(const float *buf1, size_t n, float *pdqf, cudaStream_t s)
+{
+    if (n == 0)
+        return 0;
+    int rc = upload_luts();
+    if (rc)
+        return rc;
+    dct2d_kernel<<<(unsigned)n, HT, 0, s>>>(buf1, pdqf);
+    YPDQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_gradients(const float *pdqf, size_t n, float *gradient, float *quality, cudaStream_t s)
+{
+    if (n == 0)
+        return 0;
+    pdqf_ops_kernel<<<(unsigned)n, HT, 0, s>>>(pdqf, 0, nullptr, gradient, quality, nullptr);
+    YPDQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_quantize(const float *pdqf, size_t n, float *thresholds, uint8_t *hashes, cudaStream_t s)
+{
+    if (n == 0)
+        return 0;
+    pdqf_ops_kernel<<<(unsigned)n, HT, 0, s>>>(pdqf, 1, nullptr, thresholds, nullptr, hashes);
+    YPDQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_threshold(const float *pdqf, size_t n, const float *thresholds, uint8_t *hashes,
+                     cudaStream_t s)
+{
+    if (n == 0)
+        return 0;
+    pdqf_ops_kernel<<<(unsigned)n, HT, 0, s>>>(pdqf, 2, thresholds, nullptr, nullptr, hashes);
+    YPDQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_transform(float *pdqf, size_t n, int op, cudaStream_t s)
+{
+    if (n == 0)
+        return 0;
+    pdqf_transform_kernel<<<(unsigned)n, 256, 0, s>>>(pdqf, op);
+    YPDQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_dihedrals(const float *pdqf, const float *thr0, size_t n, uint8_t *hashes, float *quality,
+                     float *thresholds, cudaStream_t s)
+{
+    if (n == 0)
+        return 0;
+    pdqf_ops_kernel<<<(unsigned)n, HT, 0, s>>>(pdqf, 3, thr0, quality, thresholds, hashes);
+    YPDQ_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace ypdq
