@@ -1,0 +1,458 @@
+#!/usr/bin/env python3
+"""bench.py -- the contract benchmark for the PDQ hash-and-match hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A *step* is one pass of the hot path over one batch of synthetic input, per GPU:
+  hash 4096 device-resident 512x512 f32 frames into 8 dihedral 256-bit hashes each
+  (BASELINE config 2), [N > 1: all-gather the 32768 x N needles over NCCL],
+  scan them against this rank's row-range shard of the 10,000,384-row x 256-bit
+  synthetic database at threshold 31 (BASELINE config 3's database; the reference
+  bench size, benches/matcher.rs:18-24), compacting every match, [N > 1: gather the
+  match lists].  metric = hash+match images/s over the whole job ("weak": frames per
+  GPU fixed, total DB fixed and sharded, so pairs per GPU stay constant).
+
+The JSON line also carries the two other figures of BASELINE.json's metric -- the
+8-needle 10M-row scan in microseconds / DB GB/s and the hash-only rate -- each with
+its roofline, a CPU baseline (the AVX2 hasher + AVX-512/u64 matcher port of the
+reference, oracle/cpu_baseline.cpp) timed on a bounded sample, the end-to-end number
+through the host-pointer C ABI, clocks sampled during the timed region and the number
+of kernels this library launched.
+
+Only this file's cpu_baseline / --impl reference legs touch oracle/ (as the measured
+CPU reference); the GPU arm never does.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "hash+match images/s vs 10M DB"
+UNIT = "images/s"
+DB_ROWS = (10_000_000 // 2048 + 1) * 2048      # 10,000,384 (benches/matcher.rs:18-24)
+FRAMES_PER_GPU = 4096
+THRESHOLD = 31
+SEED = 0x79756D652D706471
+N_PLANT = 64
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), "MEASURED_PEAKS.json", d
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# --------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (C++ port of the
+    AVX2 hasher + AVX-512 VPOPCNTDQ / u64 matcher, oracle/cpu_baseline.cpp) on all host threads.
+    Each step = a bounded sample of the workload: hash S frames, match their 8*S needles against
+    the full 10,000,384-row database."""
+    if rank != 0:
+        return
+    from oracle import pyoracle
+    pyoracle.build()
+    orc = pyoracle.get()
+    cpu = pyoracle.CpuBaseline()
+    threads = cpu.hw_threads
+    S = args.cpu_sample
+    rows = orc.synth_db(DB_ROWS, 0, SEED)
+    frames = orc.synth_frames(S, 0, SEED, 1)
+
+    def step():
+        h, q, t, _ = cpu.hash_batch(frames, threads=threads, want_pdqf=False)
+        return cpu.match(rows, h.reshape(-1, 32), THRESHOLD, True, threads)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = S * args.steps / dt
+    kind = "port"
+    sample = (f"{S} frames hashed (AVX2 port) + {8 * S} needles vs the full {DB_ROWS}-row DB per step, "
+              f"{'AVX-512 VPOPCNTDQ' if cpu.has_avx512_popcnt else 'u64 popcnt'} matcher, {threads} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+u64",
+        "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": (f"hash {FRAMES_PER_GPU} synthetic 512x512 f32 frames per GPU (8 dihedral hashes each) + "
+                     f"match all needles vs a {DB_ROWS}-row x 256-bit synthetic DB at threshold {THRESHOLD}"),
+        "frames_per_gpu": FRAMES_PER_GPU, "db_rows": DB_ROWS, "threshold": THRESHOLD,
+        "needles_per_step": FRAMES_PER_GPU * 8 * n_gpus,
+        "sharding": f"frames by batch, DB by row range over {n_gpus} GPU(s)",
+        "l2": "inputs larger than L2 (4 GiB of frames + the DB stream through the 126 MB L2 every step)",
+    }
+
+
+def cpu_baseline_leg(args):
+    """Rank 0, N=1 only: the CPU port timed on a bounded sample (about 10-30 s)."""
+    from oracle import pyoracle
+    pyoracle.build()
+    orc = pyoracle.get()
+    cpu = pyoracle.CpuBaseline()
+    threads = cpu.hw_threads
+    S = args.cpu_sample
+    rows = orc.synth_db(DB_ROWS, 0, SEED)
+    frames = orc.synth_frames(S, 0, SEED, 1)
+    t0 = time.perf_counter()
+    h, _, _, _ = cpu.hash_batch(frames, threads=threads, want_pdqf=False)
+    t1 = time.perf_counter()
+    reps = 0
+    while True:
+        cpu.match(rows, h.reshape(-1, 32), THRESHOLD, True, threads)
+        reps += 1
+        if time.perf_counter() - t1 > 8.0 or reps >= 4:
+            break
+    t2 = time.perf_counter()
+    per_step = (t1 - t0) + (t2 - t1) / reps
+    # single-thread figures comparable to the reference's published ones
+    t3 = time.perf_counter()
+    cpu.hash_batch(frames[:16], threads=1, want_pdqf=False)
+    t4 = time.perf_counter()
+    cpu.match(rows, h.reshape(-1, 32)[:8], THRESHOLD, False, 1)
+    t5 = time.perf_counter()
+    return {
+        "value": S / per_step, "unit": UNIT, "cores": threads, "kind": "port",
+        "sample": (f"{S} frames hashed + {8 * S} needles matched vs the full {DB_ROWS}-row DB, "
+                   f"AVX2 hasher port + {'AVX-512 VPOPCNTDQ' if cpu.has_avx512_popcnt else 'u64 popcnt'} "
+                   f"matcher port, {threads} threads"),
+        "hash_us_per_frame_1thread": (t4 - t3) / 16 * 1e6,
+        "scan_8_needles_ms_1thread": (t5 - t4) * 1e3,
+        "hash_images_per_s_all_threads": S / (t1 - t0),
+    }
+
+
+# --------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=256, help="frames per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    local_rank = env_int("LOCAL_RANK", 0)
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import yume_pdq_b200 as yp
+
+    if not torch.cuda.is_available() or yp.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+    B = args.frames
+    hbm_peak, peak_src, peaks = measured_peaks()
+
+    # ---- setup (untimed): inputs resident in HBM ----------------------------
+    kern = yp.CudaKernel(local_rank)
+    frames = torch.empty((B, 512, 512), dtype=torch.float32, device=dev)
+    yp.synth_frames(frames, B, first_frame=rank * B, seed=SEED, kind=1, device=local_rank)
+    from yume_pdq_b200 import sharded
+    row0, row1 = sharded.shard_range(DB_ROWS, rank, n_gpus)
+    shard_rows = row1 - row0
+    db = yp.CudaVectorDatabase(device=local_rank, global_row_offset=row0, synthetic_rows=shard_rows,
+                               seed=SEED)
+    matcher = yp.CudaMatcher(db, THRESHOLD)
+    outs = {"hashes": torch.empty((B, 8, 32), dtype=torch.uint8, device=dev),
+            "quality": torch.empty((B, 8), dtype=torch.float32, device=dev),
+            "thresholds": torch.empty((B, 8), dtype=torch.float32, device=dev)}
+    q_all = B * 8 * n_gpus
+    needles_all = torch.empty((q_all, 32), dtype=torch.uint8, device=dev)
+    CAP = 1 << 16
+    match_out = torch.zeros((CAP, 16), dtype=torch.uint8, device=dev)
+    match_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    gathered = torch.empty((n_gpus, CAP // 16, 16), dtype=torch.uint8, device=dev) if n_gpus > 1 else None
+    gathered_cnt = torch.empty(n_gpus, dtype=torch.int32, device=dev) if n_gpus > 1 else None
+
+    # plant rows so the scan has something to find: copies of this job's own hashes, 0..31 bits away
+    kern.hash_batch(frames, out=outs)
+    torch.cuda.synchronize()
+    local_hashes = outs["hashes"].reshape(-1, 32).cpu().numpy()
+    rng = np.random.default_rng(1234 + rank)
+    planted = []
+    for k in range(N_PLANT):
+        j = int(rng.integers(0, local_hashes.shape[0]))
+        lrow = int(rng.integers(0, shard_rows))
+        h = np.unpackbits(local_hashes[j].copy())
+        flips = rng.choice(256, size=int(rng.integers(0, 32)), replace=False)
+        h[flips] ^= 1
+        db.write_rows(lrow, np.packbits(h)[None])
+        planted.append((row0 + lrow, rank * B * 8 + j))
+
+    def step():
+        kern.hash_batch(frames, out=outs)
+        if n_gpus > 1:
+            dist.all_gather_into_tensor(needles_all, outs["hashes"].reshape(-1, 32))
+            nd = needles_all
+        else:
+            nd = outs["hashes"].reshape(-1, 32)
+        match_cnt.zero_()
+        matcher.find_device(nd, q_all, match_out, CAP, match_cnt, algo=yp.ALGO_AUTO)
+        if n_gpus > 1:   # gather of the (small, fixed-capacity) match lists: the only exchange besides the needles
+            dist.all_gather_into_tensor(gathered_cnt, match_cnt)
+            dist.all_gather_into_tensor(gathered.reshape(-1, 16), match_out[: CAP // 16])
+
+    def barrier():
+        if n_gpus > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    # ---- timed region ----------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.25)
+    launches0 = yp.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+    launches = yp.launch_count() - launches0
+    clocks = sampler.stop()
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    lt = torch.tensor([launches], dtype=torch.int64, device=dev)
+    if n_gpus > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = n_gpus * B / (ms_per_step * 1e-3)
+
+    # ---- correctness of what was timed (untimed check) -----------------------
+    n_matches = int(match_cnt.item())
+    got = match_out[:min(n_matches, CAP)].cpu().numpy().view(yp.MATCH_DTYPE).reshape(-1)
+    got_set = {(int(r), int(n)) for r, n in zip(got["row"], got["needle"])}
+    missing = [p for p in planted if p not in got_set]
+    if missing:
+        raise SystemExit(f"bench.py: rank {rank}: {len(missing)} planted matches were not found")
+
+    # ---- per-kernel timings for the rooflines (CUDA events on the launch stream) ------
+    def time_kernel(fn, iters, flush=None):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            if flush is not None:
+                flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts)), float(np.median(ts)), float(np.min(ts))
+
+    line_extra = {}
+    if rank == 0:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        nd = outs["hashes"].reshape(-1, 32)
+        # (1) dominant kernel of the step: large-batch match (INT/XU-pipe bound)
+        m_mean, m_med, _ = time_kernel(
+            lambda: (match_cnt.zero_(), matcher.find_device(nd, B * 8, match_out, CAP, match_cnt)), 3)
+        pairs = shard_rows * B * 8
+        sm_mhz = clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
+        xu_peak = 148 * 16 * sm_mhz * 1e6 / 2 / 1e12      # Tpairs/s at 2 POPC per pair, 16 POPC/clk/SM
+        # (2) hash kernel (HBM bound): algorithmic bytes = frames in + hashes/quality/thresholds out
+        h_mean, h_med, h_min = time_kernel(lambda: kern.hash_batch(frames, out=outs), 10, flush)
+        hash_bytes = B * (512 * 512 * 4 + 8 * 32 + 8 * 4 + 8 * 4)
+        # (3) headline scan: 8 needles vs the resident shard (HBM bound), L2 flushed between launches
+        n8 = nd[:8].contiguous()
+        s_mean, s_med, s_min = time_kernel(
+            lambda: matcher.find_device(n8, 8, match_out, CAP, match_cnt), 20, flush)
+        scan_bytes = shard_rows * 32
+        share = m_mean / (m_mean + h_mean)
+        line_extra["roofline"] = {
+            "kernel": "match_tiled_kernel (needle batch 32768 x this rank's DB shard)",
+            "bound": "int",
+            "achieved": pairs / (m_mean * 1e-3) / 1e12, "peak": xu_peak, "unit": "Tpairs/s",
+            "frac": pairs / (m_mean * 1e-3) / 1e12 / xu_peak,
+            "peak_source": ("POPC (XU) pipe: 148 SMs x 16 POPC/clk x median SM clock under load / 2 POPC per "
+                            "pair; no entry for an integer pipe exists in MEASURED_PEAKS.json"),
+            "traffic": None, "ms_per_launch": m_mean, "share_of_step": share,
+        }
+        line_extra["roofline_hash"] = {
+            "kernel": "hash_fused_kernel", "bound": "hbm", "achieved": hash_bytes / (h_mean * 1e-3) / 1e9,
+            "peak": hbm_peak, "unit": "GB/s", "frac": hash_bytes / (h_mean * 1e-3) / 1e9 / hbm_peak,
+            "peak_source": peak_src, "traffic": None, "ms_per_launch": h_mean,
+            "images_per_s": B / (h_mean * 1e-3),
+        }
+        line_extra["scan"] = {
+            "kernel": "8 needles x %d rows, threshold %d" % (shard_rows, THRESHOLD),
+            "us": s_mean * 1e3, "us_median": s_med * 1e3, "us_min": s_min * 1e3,
+            "db_gbs": scan_bytes / (s_mean * 1e-3) / 1e9, "bound": "hbm", "peak": hbm_peak,
+            "frac": scan_bytes / (s_mean * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src,
+            "rows_per_s": shard_rows / (s_mean * 1e-3), "traffic": None,
+        }
+        del flush
+
+    # ---- end to end through the host-pointer C ABI ---------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(1, min(args.steps, 3))
+        host_frames = torch.empty((B, 512, 512), dtype=torch.float32, pin_memory=True)
+        host_frames.copy_(frames)
+        host_hashes = np.zeros((B, 8, 32), dtype=np.uint8)
+        hk = yp.CudaKernel(local_rank)
+
+        def e2e_step():
+            hk.hash_batch(host_frames.numpy(), want_quality=False, want_thresholds=False,
+                          out={"hashes": host_hashes})
+            needles = host_hashes.reshape(-1, 32)
+            if n_gpus > 1:
+                nt = torch.from_numpy(needles).to(dev)
+                dist.all_gather_into_tensor(needles_all, nt)
+                return matcher.find_all(needles_all)
+            return matcher.find_all(needles)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            m = e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if n_gpus > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": n_gpus * B * e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(B * 512 * 512 * 4 + B * 8 * 32),
+               "d2h_bytes_per_step": int(B * 8 * 32 + 16 + len(m) * 16),
+               "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
+               "path": "yume_pdq_cuda_hash_batch(host frames) + yume_pdq_cuda_matcher_find(host needles)"}
+        del host_frames
+
+    cpu_bl = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        cpu_bl = cpu_baseline_leg(args)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (hash) / u32 popcount (match)",
+            "data": "synthetic", "config": workload_config(n_gpus),
+            "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks,
+            "matches_per_step": n_matches, "planted": N_PLANT,
+            "cpu_baseline": cpu_bl,
+        }
+        line.update(line_extra)
+        print(json.dumps(line), flush=True)
+    db.close()
+    if n_gpus > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -49,6 +49,14 @@ struct Luts {
         std::memcpy(dct, YUME_PDQ_DCT_MATRIX_BITS, sizeof(uint32_t) * 16 * 127);
         for (int i = 0; i < 7; i++)
             std::memcpy(tent_x8 + 8 * i, YUME_PDQ_TENT_WEIGHT_BITS + 7 * i, sizeof(uint32_t) * 7);
+        // The LUT carries two ~1e-40 (subnormal) residues at [0][4], [0][5] (oracle/lut_gen.py).
+        // On Intel hosts every FMA touching them takes a microcode assist and the tent filter
+        // runs ~20x slower than the reference publishes (27.6 us, bench.csv:8, measured on
+        // Zen 4).  They cannot change any result for non-degenerate images, so the TIMED
+        // baseline drops them -- this only makes the CPU baseline faster.
+        for (int i = 0; i < 7 * 8; i++)
+            if (std::fabs(tent_x8[i]) < 1e-30f)
+                tent_x8[i] = 0.0f;
     }
 };
 const Luts &luts()
@@ -119,37 +127,49 @@ AVX2 inline float hmin(__m256 a)
 }
 
 // ---- x86.rs:100-281 -------------------------------------------------------
-// two alternating FMA accumulators in the pattern 1,0,0,1,1,0,0,1 per 8 steps
+// two alternating FMA accumulators in the pattern 1,0,0,1,1,0,0,1 per 8 steps (unrolled so they
+// stay in registers, as the reference's macro expansion does)
 AVX2 void dct2d_avx2(const float *buf /*[128][128]*/, float *tmp /*[128]*/, float *pdqf)
 {
     const float *D = luts().dct;
-    static const int target[8] = {1, 0, 0, 1, 1, 0, 0, 1};
     for (int k = 0; k < 16; k++) {
+        const float *dk = D + k * 127;
         for (int j8 = 0; j8 < 128; j8 += 8) {
-            __m256 s[2] = {_mm256_setzero_ps(), _mm256_setzero_ps()};
-            for (int k2 = 0; k2 < 128; k2++) {
-                __m256 row = _mm256_loadu_ps(buf + k2 * 128 + j8);
-                __m256 d = _mm256_set1_ps(D[k * 127 + k2]);
-                int t = target[k2 & 7];
-                s[t] = _mm256_fmadd_ps(row, d, s[t]);
+            __m256 s0 = _mm256_setzero_ps(), s1 = _mm256_setzero_ps();
+            const float *b = buf + j8;
+#define STEP(acc, K2) acc = _mm256_fmadd_ps(_mm256_loadu_ps(b + (K2) * 128), _mm256_set1_ps(dk[K2]), acc)
+            for (int k2 = 0; k2 < 128; k2 += 8) {  // accumulator pattern 1,0,0,1,1,0,0,1 (x86.rs:170-204)
+                STEP(s1, k2 + 0);
+                STEP(s0, k2 + 1);
+                STEP(s0, k2 + 2);
+                STEP(s1, k2 + 3);
+                STEP(s1, k2 + 4);
+                STEP(s0, k2 + 5);
+                STEP(s0, k2 + 6);
+                STEP(s1, k2 + 7);
             }
+#undef STEP
             __m256 z = _mm256_setzero_ps();
-            __m256 m0 = _mm256_cmp_ps(s[0], z, _CMP_ORD_S);
-            __m256 m1 = _mm256_cmp_ps(s[1], z, _CMP_ORD_S);
-            __m256 a0 = _mm256_blendv_ps(z, s[0], m0);
-            __m256 a1 = _mm256_blendv_ps(z, s[1], m1);
+            __m256 a0 = _mm256_blendv_ps(z, s0, _mm256_cmp_ps(s0, z, _CMP_ORD_S));
+            __m256 a1 = _mm256_blendv_ps(z, s1, _mm256_cmp_ps(s1, z, _CMP_ORD_S));
             _mm256_storeu_ps(tmp + j8, _mm256_add_ps(a0, a1));
         }
         for (int j = 0; j < 16; j++) {
-            __m256 s[2] = {_mm256_setzero_ps(), _mm256_setzero_ps()};
+            __m256 s0 = _mm256_setzero_ps(), s1 = _mm256_setzero_ps();
             const float *dr = D + j * 127;
-            for (int c = 0; c < 16; c++) {
-                __m256 t = _mm256_loadu_ps(tmp + 8 * c);
-                __m256 d = _mm256_loadu_ps(dr + 8 * c);
-                int tg = target[c & 7];
-                s[tg] = _mm256_fmadd_ps(t, d, s[tg]);
+#define STEP(acc, C) acc = _mm256_fmadd_ps(_mm256_loadu_ps(tmp + 8 * (C)), _mm256_loadu_ps(dr + 8 * (C)), acc)
+            for (int c = 0; c < 16; c += 8) {
+                STEP(s1, c + 0);
+                STEP(s0, c + 1);
+                STEP(s0, c + 2);
+                STEP(s1, c + 3);
+                STEP(s1, c + 4);
+                STEP(s0, c + 5);
+                STEP(s0, c + 6);
+                STEP(s1, c + 7);
             }
-            pdqf[k * 16 + j] = hsum(_mm256_add_ps(s[0], s[1]));
+#undef STEP
+            pdqf[k * 16 + j] = hsum(_mm256_add_ps(s0, s1));
         }
     }
 }

