@@ -1,0 +1,38 @@
+//! Raw bindings of include/yume_pdq_cuda.h (group B).  NOT COMPILED in the build image.
+#![allow(non_camel_case_types)]
+use core::ffi::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct YumePDQ_CudaDb { _private: [u8; 0] }
+
+#[repr(C)]
+#[derive(Debug, Clone, Copy, PartialEq, Eq, Default)]
+pub struct YumePDQ_Match { pub row: u64, pub needle: u32, pub dist: u32 }
+
+pub const E_CAPACITY: c_int = -3;
+
+unsafe extern "C" {
+    pub fn yume_pdq_cuda_error_string(code: c_int) -> *const c_char;
+    pub fn yume_pdq_cuda_device_count() -> c_int;
+    pub fn yume_pdq_cuda_kernel_ident() -> *const c_char;
+    pub fn yume_pdq_cuda_hash_batch(device: c_int, frames: *const f32, n: usize, hashes: *mut u8,
+        quality: *mut f32, thresholds: *mut f32, pdqf: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn yume_pdq_cuda_jarosz_compress(device: c_int, frames: *const f32, n: usize, buf1: *mut f32,
+        stream: *mut c_void) -> c_int;
+    pub fn yume_pdq_cuda_dct2d(device: c_int, buf1: *const f32, n: usize, pdqf: *mut f32,
+        stream: *mut c_void) -> c_int;
+    pub fn yume_pdq_cuda_sum_of_gradients(device: c_int, pdqf: *const f32, n: usize, gradient: *mut f32,
+        quality: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn yume_pdq_cuda_quantize(device: c_int, pdqf: *const f32, n: usize, thresholds: *mut f32,
+        hashes: *mut u8, stream: *mut c_void) -> c_int;
+    pub fn yume_pdq_cuda_pdqf_transform(device: c_int, pdqf: *mut f32, n: usize, op: c_int,
+        stream: *mut c_void) -> c_int;
+    pub fn yume_pdq_cuda_db_create(device: c_int, rows: *const u8, n_rows: usize, global_row_offset: u64,
+        out: *mut *mut YumePDQ_CudaDb) -> c_int;
+    pub fn yume_pdq_cuda_db_destroy(db: *mut YumePDQ_CudaDb) -> c_int;
+    pub fn yume_pdq_cuda_db_len(db: *const YumePDQ_CudaDb) -> usize;
+    pub fn yume_pdq_cuda_matcher_scan(db: *mut YumePDQ_CudaDb, needles: *const u8, q: usize, threshold: u32,
+        matched: *mut c_int, stream: *mut c_void) -> c_int;
+    pub fn yume_pdq_cuda_matcher_find(db: *mut YumePDQ_CudaDb, needles: *const u8, q: usize, threshold: u32,
+        out: *mut YumePDQ_Match, cap: usize, n_found: *mut usize, stream: *mut c_void) -> c_int;
+}
