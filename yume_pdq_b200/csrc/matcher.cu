@@ -425,6 +425,9 @@ int launch_match(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const 
     }
     if (algo == YUME_PDQ_CUDA_ALGO_STREAM && q > ST_MAXQ)
         algo = YUME_PDQ_CUDA_ALGO_TILED;
+    if (algo == YUME_PDQ_CUDA_ALGO_TENSOR)
+        return launch_match_tensor(rows, n_rows, row_offset, needles, q, threshold, out, cap, count, min_key,
+                                   mode, sm_count, s);
 
     if (algo == YUME_PDQ_CUDA_ALGO_EXACT) {
         dim3 grid((unsigned)((n_rows + EX_THREADS * EX_ROWS - 1) / (EX_THREADS * EX_ROWS)),
