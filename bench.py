@@ -337,19 +337,23 @@ def main():
 
     # ---- per-kernel timings for the rooflines (CUDA events on the launch stream) ------
     def time_kernel(fn, iters, flush=None):
+        """CUDA events on the launch stream.  The whole sequence [flush, e0, kernel, e1] x iters is
+        enqueued without host synchronisation, so the GPU never waits for the host between the
+        event and the kernel (a host-paced loop adds ~10 us of launch latency to every sample)."""
         for _ in range(2):
             fn()
         torch.cuda.synchronize()
-        ts = []
-        for _ in range(iters):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        if flush is not None:
+            flush.zero_()
+        for a, b in ev:
             if flush is not None:
                 flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             fn()
             b.record()
-            torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b))
+        torch.cuda.synchronize()
+        ts = [a.elapsed_time(b) for a, b in ev]
         return float(np.mean(ts)), float(np.median(ts)), float(np.min(ts))
 
     line_extra = {}

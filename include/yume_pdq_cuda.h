@@ -177,7 +177,8 @@ int yume_pdq_cuda_db_write_rows(YumePDQ_CudaDb *db, size_t first_local_row, cons
 #define YUME_PDQ_CUDA_ALGO_EXACT 1   /* unfiltered: 8 POPC per (row, needle) pair */
 #define YUME_PDQ_CUDA_ALGO_TILED 2   /* rows in registers x needles in smem, 96-bit carry-save prefilter */
 #define YUME_PDQ_CUDA_ALGO_STREAM 3  /* TMA bulk-copy ring + prefilter, needle prefixes in registers (q <= 32) */
-#define YUME_PDQ_CUDA_ALGO_TENSOR 4  /* tcgen05.mma kind::i8 on +-1 expanded bits: large needle batches */
+#define YUME_PDQ_CUDA_ALGO_TENSOR 4  /* tcgen05.mma kind::mxf4 on +-1.0 e2m1 expanded bits (thresholds > 127: kind::i8): large needle batches */
+#define YUME_PDQ_CUDA_ALGO_TENSOR_I8 5  /* tcgen05.mma kind::i8 on +-1 int8 expanded bits, any threshold */
 
 /* PDQMatcher::scan (matching/mod.rs:72-79): *matched = 1 iff any needle is within
  * `threshold` (inclusive) of any row.  needles q x 32 bytes, host or device. */

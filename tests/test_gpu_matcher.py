@@ -38,7 +38,7 @@ def test_planted_vs_oracle_all_algos(cuda, oracle, n_rows, q):
     assert match_tuples(m.find_all(needles)) == want          # sorted (row, needle) like CpuMatcher::find
     assert m.scan(needles) == (len(want) > 0)
     assert m.find_min(needles) == oracle.matcher_find_min(rows, needles, 31)
-    for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_STREAM, cuda.ALGO_TENSOR):
+    for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_STREAM, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8):
         assert _find_device(cuda, m, needles, algo) == sorted(want), algo
     db.close()
 
@@ -63,6 +63,7 @@ def test_thresholds(cuda, oracle, threshold):
             assert _find_device(cuda, m, needles, algo, cap=1 << 18) == sorted(want)
     if len(want) < 200_000:     # the tensor-core path has no prefilter: exact for every threshold
         assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR, cap=1 << 18) == sorted(want)
+        assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_I8, cap=1 << 18) == sorted(want)
     db.close()
 
 
@@ -104,6 +105,7 @@ def test_large_needle_batch_multi_chunk(cuda, oracle):
     assert _find_device(cuda, m, needles, cuda.ALGO_EXACT) == sorted(want)
     assert _find_device(cuda, m, needles, cuda.ALGO_TILED) == sorted(want)
     assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR) == sorted(want)
+    assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_I8) == sorted(want)
     db.close()
 
 
@@ -121,7 +123,7 @@ def test_adversarial_dense_matches(cuda, oracle):
     m = cuda.CudaMatcher(db, 31)
     got = m.find_all(needles, cap=1000)        # forces the E_CAPACITY retry path
     assert match_tuples(got) == want
-    for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_TENSOR):
+    for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8):
         assert _find_device(cuda, m, needles, algo, cap=1 << 19) == sorted(want)
     assert _find_device(cuda, m, needles[:32], cuda.ALGO_STREAM, cap=1 << 19) == sorted(
         t for t in want if t[1] < 32)
@@ -185,7 +187,7 @@ def test_headline_config_10m(cuda, oracle):
     want = sorted(p for p in planted if p[2] <= 31)
     assert match_tuples(m.find_all(needles)) == want
     assert m.find_min(needles) == (want[0][0], want[0][1])
-    for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_STREAM, cuda.ALGO_TENSOR):
+    for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_STREAM, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8):
         assert _find_device(cuda, m, needles, algo) == want
     # last rows of the last chunk are planted too (tail handling)
     db.write_rows(n - 1, needles[5][None])

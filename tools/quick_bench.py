@@ -55,9 +55,9 @@ def main():
         m = yp.CudaMatcher(db, 31)
         out = torch.zeros((1 << 20, 16), dtype=torch.uint8, device="cuda")
         cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
-        for q in (128, 1024, 8192, 32768):
+        for q in (512, 1024, 4096, 32768):
             needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
-            for name, algo in (("tensor", yp.ALGO_TENSOR), ("tiled", yp.ALGO_TILED)):
+            for name, algo in (("mxf4", yp.ALGO_TENSOR), ("i8", yp.ALGO_TENSOR_I8), ("tiled", yp.ALGO_TILED)):
                 med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 20, cnt, algo=algo), iters=3, warm=1)
                 print(f"match 10M x {q:6d} {name:6s}: median {med / 1e3:9.2f} ms  {n * q / med / 1e6:8.3f} Tpairs/s  "
                       f"hits={int(cnt.item())}")

@@ -27,7 +27,7 @@ LIB_PATH = os.path.join(HERE, "libyume_pdq_cuda.so")
 
 MATCH_DTYPE = np.dtype([("row", "<u8"), ("needle", "<u4"), ("dist", "<u4")])
 
-ALGO_AUTO, ALGO_EXACT, ALGO_TILED, ALGO_STREAM, ALGO_TENSOR = 0, 1, 2, 3, 4
+ALGO_AUTO, ALGO_EXACT, ALGO_TILED, ALGO_STREAM, ALGO_TENSOR, ALGO_TENSOR_I8 = 0, 1, 2, 3, 4, 5
 
 OP_T = 0
 OP_NEGATE_ALT_COLS_FALSE = 1

@@ -416,16 +416,23 @@ int launch_match(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const 
     const uint4 *rows4 = reinterpret_cast<const uint4 *>(rows);
     const uint4 *needles4 = reinterpret_cast<const uint4 *>(needles);
     if (algo == YUME_PDQ_CUDA_ALGO_AUTO) {
-        // the 96-bit prefix bound stops filtering once threshold approaches 48 (= 96/2)
-        // (measured on B200, 10M rows x 8 needles: tiled 68.7 us, stream 80.9 us, exact 156.7 us)
-        if (threshold > 40)
+        // Measured on B200 (10M rows): 8 needles tiled 58 us / stream 80 us / exact 157 us; 1024 needles
+        // tensor 3.8 ms vs tiled 4.7 ms; 128 needles tiled 0.60 ms vs tensor 0.69 ms.  The tensor-core
+        // kernels amortise one row-tile expansion over q / 128 needle tiles, so they win for large batches;
+        // the 96-bit prefix bound of the POPC kernels stops filtering once threshold approaches 48.
+        if (q >= 512)
+            algo = YUME_PDQ_CUDA_ALGO_TENSOR;
+        else if (threshold > 40)
             algo = YUME_PDQ_CUDA_ALGO_EXACT;
         else
             algo = YUME_PDQ_CUDA_ALGO_TILED;
     }
     if (algo == YUME_PDQ_CUDA_ALGO_STREAM && q > ST_MAXQ)
         algo = YUME_PDQ_CUDA_ALGO_TILED;
-    if (algo == YUME_PDQ_CUDA_ALGO_TENSOR)
+    if (algo == YUME_PDQ_CUDA_ALGO_TENSOR && threshold <= 127)
+        return launch_match_tensor4(rows, n_rows, row_offset, needles, q, threshold, out, cap, count, min_key,
+                                    mode, sm_count, s);
+    if (algo == YUME_PDQ_CUDA_ALGO_TENSOR || algo == YUME_PDQ_CUDA_ALGO_TENSOR_I8)
         return launch_match_tensor(rows, n_rows, row_offset, needles, q, threshold, out, cap, count, min_key,
                                    mode, sm_count, s);
 

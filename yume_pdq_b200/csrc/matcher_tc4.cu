@@ -1,0 +1,461 @@
+// matcher_tc4.cu -- tensor-core Hamming matcher, packed-FP4 formulation (tcgen05.mma kind::mxf4).
+//
+// Same contract as matcher.cu (reference src/matching/mod.rs:336-362: every (row, needle) with
+// popcount(row ^ needle) <= threshold, bit-exact).  Bits are mapped to e2m1 +-1.0 (nibbles 0x2 / 0xA), all
+// ue8m0 block scales are 1.0, accumulation is f32 (exact: |dot| <= 256), so
+//     dot(needle, row) = 256 - 2 * hamming(needle, row).
+// Packed FP4 halves the operand bytes and doubles the MMA rate relative to the kind::i8 formulation of
+// matcher_tc.cu (measured issue rate on B200: 8.9 POPS vs 4.55 POPS, tools/mma_peak.cu), i.e. a ceiling
+// of 17.4e12 (row, needle) pairs/s instead of 8.9e12.
+//
+// Persistent kernel, one CTA per SM, 12 warps, warp-specialised:
+//   warp 0       A producer: streams pre-expanded needle tiles (128 needles x 128 B = 16 KB, canonical
+//                K-major SWIZZLE_NONE layout) from L2 into a 4-stage shared-memory ring with TMA bulk copies
+//   warp 1       MMA issuer: per (needle tile, row tile) 4 x tcgen05.mma (M 128, N 240, K 64) into one of two
+//                240-column TMEM accumulators; tcgen05.commit -> mbarriers
+//   warps 2-3    B expanders: turn the CTA's next 480 database rows (15 KB of bits) into two 30 KB e2m1
+//                row tiles (double buffered); each needle tile is streamed ONCE per 480 rows
+//   warps 4-11   epilogue: tcgen05.ld (lane = needle, column = row), 3-input max tree over the raw f32
+//                bits, rare hit path with exact distance = (256 - dot) / 2
+// Shared memory: 2 x 60 KB (B) + 4 x 16 KB (A) = 184 KB.  TMEM: 2 x 240 accumulator columns + 32 columns
+// of scale factors (every byte 0x7F = 2^0, so the scale-factor layout is irrelevant).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace ypdq {
+namespace {
+
+constexpr int T4_M = 128;                  // needles per tile (TMEM lanes)
+constexpr int T4_N = 240;                  // rows per tile (TMEM columns)
+constexpr int T4_NB = 2;                   // row tiles per super-tile (needle tile reuse)
+constexpr int T4_ROWS = T4_N * T4_NB;      // 480 rows per super-tile
+constexpr int T4_ROW_BYTES = 128;          // 256 e2m1 nibbles
+constexpr int T4_A_BYTES = T4_M * T4_ROW_BYTES;      // 16 KB
+constexpr int T4_B_BYTES = T4_N * T4_ROW_BYTES;      // 30 KB
+constexpr int T4_SB_BYTES = T4_NB * T4_B_BYTES;      // 60 KB per super-tile buffer
+constexpr int T4_A_STAGES = 4;
+constexpr int T4_EPI_WARPS = 8;
+constexpr int T4_EXP_THREADS = 64;          // B expander threads (warps 2-3)
+constexpr int T4_THREADS = 64 + T4_EXP_THREADS + 32 * T4_EPI_WARPS;  // 384 -> up to 168 registers per thread
+constexpr uint32_t T4_LBO = 128;           // bytes between K-adjacent core matrices (16-byte chunks)
+constexpr uint32_t T4_SBO = 1024;          // bytes between 8-row groups
+constexpr uint32_t T4_SF_COL = 480;        // TMEM columns 480..511: scale factors
+constexpr size_t T4_SMEM = 2 * (size_t)T4_SB_BYTES + T4_A_STAGES * (size_t)T4_A_BYTES + 256;
+
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t *b, uint32_t n)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(n));
+}
+__device__ __forceinline__ void bar_arrive(uint64_t *b)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t *b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool bar_try(uint64_t *b, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(s32(b)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void bar_wait(uint64_t *b, uint32_t parity)
+{
+    while (!bar_try(b, parity)) {
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *b)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)),
+                 "l"(src), "r"(bytes), "r"(s32(b))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *b)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(b)) : "memory");
+}
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr)
+{
+    // K-major, SWIZZLE_NONE canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte units; version 1
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (uint64_t)(T4_LBO >> 4) << 16 | (uint64_t)(T4_SBO >> 4) << 32 |
+           (uint64_t)1 << 46;
+}
+// block-scaled instruction descriptor: A = B = e2m1 (MXF4 format 1), both K-major, ue8m0 scales,
+// N = 240, M = 128, K = 64 (dense), scale-factor ids 0
+constexpr uint32_t T4_IDESC = (1u << 7) | (1u << 10) | ((uint32_t)(T4_N >> 3) << 17) | (1u << 23) |
+                              ((uint32_t)(T4_M >> 4) << 24);
+
+// 8 bits -> 8 e2m1 nibbles: bit i -> nibble i; bit 1 -> 0x2 (+1.0), bit 0 -> 0xA (-1.0)
+__device__ __forceinline__ uint32_t expand8(uint32_t x)
+{
+    x = (x | (x << 12)) & 0x000F000Fu;
+    x = (x | (x << 6)) & 0x03030303u;
+    x = (x | (x << 3)) & 0x11111111u;
+    return (x << 3) ^ 0xAAAAAAAAu;
+}
+// one 32-bit hash word -> one 16-byte K chunk (32 e2m1 elements)
+__device__ __forceinline__ uint4 expand32(uint32_t w)
+{
+    return make_uint4(expand8(w & 255u), expand8((w >> 8) & 255u), expand8((w >> 16) & 255u), expand8(w >> 24));
+}
+// canonical tile offset of (row r, 16-byte chunk kc)
+__device__ __forceinline__ uint32_t tile_off(uint32_t r, uint32_t kc)
+{
+    return (r >> 3) * T4_SBO + kc * T4_LBO + (r & 7u) * 16u;
+}
+
+// needles (q x 32 B) -> n_tiles tiles of 16 KB in the canonical layout; padding needles expand from zero bits
+__global__ void __launch_bounds__(256)
+expand_needles4_kernel(const uint4 *__restrict__ needles, uint32_t q, uint8_t *__restrict__ out, uint32_t n_tiles)
+{
+    const uint32_t idx = blockIdx.x * 256 + threadIdx.x;  // one thread per (needle, half)
+    const uint32_t j = idx >> 1, half = idx & 1u;
+    if (j >= n_tiles * T4_M)
+        return;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (j < q)
+        v = __ldg(needles + 2 * (size_t)j + half);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint8_t *tile = out + (size_t)(j / T4_M) * T4_A_BYTES;
+    const uint32_t r = j % T4_M;
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+        *reinterpret_cast<uint4 *>(tile + tile_off(r, 4 * half + c)) = expand32(w[c]);
+}
+
+struct Tc4Sink {
+    YumePDQ_Match *out;
+    uint32_t cap;
+    uint32_t *count;
+    unsigned long long *min_key;
+    uint64_t row_offset;
+    uint64_t q;
+    int mode;
+};
+
+__device__ __forceinline__ void tc4_emit(const Tc4Sink &k, uint64_t local_row, uint32_t needle, uint32_t dist)
+{
+    uint32_t pos = atomicAdd(k.count, 1u);
+    if (k.mode == MODE_MIN) {
+        atomicMin(k.min_key, (unsigned long long)(local_row * k.q + needle));
+    } else if (pos < k.cap) {
+        YumePDQ_Match m;
+        m.row = local_row + k.row_offset;
+        m.needle = needle;
+        m.dist = dist;
+        k.out[pos] = m;
+    }
+}
+
+#define T4_LD_X32(v, o, taddr)                                                                                 \
+    asm volatile(                                                                                              \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                              \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                             \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"              \
+        : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]),      \
+          "=r"(v[o + 6]), "=r"(v[o + 7]), "=r"(v[o + 8]), "=r"(v[o + 9]), "=r"(v[o + 10]), "=r"(v[o + 11]),    \
+          "=r"(v[o + 12]), "=r"(v[o + 13]), "=r"(v[o + 14]), "=r"(v[o + 15]), "=r"(v[o + 16]), "=r"(v[o + 17]), \
+          "=r"(v[o + 18]), "=r"(v[o + 19]), "=r"(v[o + 20]), "=r"(v[o + 21]), "=r"(v[o + 22]), "=r"(v[o + 23]), \
+          "=r"(v[o + 24]), "=r"(v[o + 25]), "=r"(v[o + 26]), "=r"(v[o + 27]), "=r"(v[o + 28]), "=r"(v[o + 29]), \
+          "=r"(v[o + 30]), "=r"(v[o + 31])                                                                     \
+        : "r"(taddr))
+#define T4_LD_X16(v, o, taddr)                                                                                 \
+    asm volatile(                                                                                              \
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                              \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                       \
+        : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]),      \
+          "=r"(v[o + 6]), "=r"(v[o + 7]), "=r"(v[o + 8]), "=r"(v[o + 9]), "=r"(v[o + 10]), "=r"(v[o + 11]),    \
+          "=r"(v[o + 12]), "=r"(v[o + 13]), "=r"(v[o + 14]), "=r"(v[o + 15])                                   \
+        : "r"(taddr))
+#define T4_LD_X8(v, o, taddr)                                                                                  \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"               \
+                 : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), \
+                   "=r"(v[o + 6]), "=r"(v[o + 7])                                                              \
+                 : "r"(taddr))
+#define T4_LD_X4(v, o, taddr)                                                                                  \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"                               \
+                 : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3])                              \
+                 : "r"(taddr))
+
+constexpr int T4_EW = T4_N / 2;      // 120 columns per epilogue warp
+constexpr int T4_EB = T4_EW / 2;     // 60 columns per register batch
+
+// 60 consecutive accumulator columns of this warp's 32 lanes -> v[0..59] (asynchronous; needs wait::ld)
+__device__ __forceinline__ void load_batch(int32_t (&v)[T4_EB], uint32_t taddr)
+{
+    T4_LD_X32(v, 0, taddr);
+    T4_LD_X16(v, 32, taddr + 32);
+    T4_LD_X8(v, 48, taddr + 48);
+    T4_LD_X4(v, 56, taddr + 56);
+}
+
+// v holds raw f32 bits of exact integer dot products.  For dot_min > 0 a signed-integer compare of the raw
+// bits against the bits of dot_min is the f32 compare (all non-negative floats order like their bits and
+// every negative float has the sign bit set).
+__device__ __forceinline__ void process_batch(const int32_t (&v)[T4_EB], int32_t min_bits, uint64_t row0,
+                                              uint64_t n_rows, uint32_t needle, uint32_t q, const Tc4Sink &sink)
+{
+    int32_t mx = v[0];
+#pragma unroll
+    for (int j = 1; j < T4_EB; j++)
+        mx = max(mx, v[j]);
+    if (mx >= min_bits && needle < q) {  // rare: some row of this batch matches this needle
+#pragma unroll
+        for (int j = 0; j < T4_EB; j++) {
+            if (v[j] >= min_bits) {
+                const uint64_t row = row0 + j;
+                if (row < n_rows) {
+                    const int32_t dot = (int32_t)__int_as_float(v[j]);
+                    tc4_emit(sink, row, needle, (uint32_t)(256 - dot) >> 1);
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(T4_THREADS, 1)
+match_tensor4_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint8_t *__restrict__ needles_exp,
+                     uint32_t n_mtiles, uint32_t q, int32_t min_bits, Tc4Sink sink)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t *sB = smem;                                    // 2 x 60 KB
+    uint8_t *sA = smem + 2 * T4_SB_BYTES;                  // 4 x 16 KB
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sA + T4_A_STAGES * T4_A_BYTES);
+    uint64_t *a_full = bars, *a_empty = bars + 4, *b_full = bars + 8, *b_empty = bars + 10;
+    uint64_t *d_full = bars + 12, *d_empty = bars + 14;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 16);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < T4_A_STAGES; i++) {
+            bar_init(&a_full[i], 1);
+            bar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            bar_init(&b_full[i], T4_EXP_THREADS);
+            bar_init(&b_empty[i], 1);
+            bar_init(&d_full[i], 1);
+            bar_init(&d_empty[i], T4_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    if (warp >= 4 && warp < 8) {
+        // scale factors: ue8m0 0x7F = 1.0 in every byte of columns 480..511 of all 128 lanes
+        const uint32_t base = tmem + (((uint32_t)(warp & 3) * 32u) << 16) + T4_SF_COL;
+        const uint32_t one = 0x7F7F7F7Fu;
+#pragma unroll 1
+        for (uint32_t c = 0; c < 32; c++)
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(base + c), "r"(one) : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    const uint64_t n_stiles = (n_rows + T4_ROWS - 1) / T4_ROWS;
+
+    if (warp == 0) {
+        // ===== A producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint64_t st = blockIdx.x; st < n_stiles; st += gridDim.x)
+                for (uint32_t m = 0; m < n_mtiles; m++, it++) {
+                    const uint32_t s = it % T4_A_STAGES, use = it / T4_A_STAGES;
+                    bar_wait(&a_empty[s], (use & 1u) ^ 1u);
+                    bar_expect_tx(&a_full[s], T4_A_BYTES);
+                    bulk_g2s(sA + (size_t)s * T4_A_BYTES, needles_exp + (size_t)m * T4_A_BYTES, T4_A_BYTES, &a_full[s]);
+                }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t ia = 0, id = 0, i = 0;
+            for (uint64_t st = blockIdx.x; st < n_stiles; st += gridDim.x, i++) {
+                const uint32_t b = i & 1u;
+                bar_wait(&b_full[b], (i >> 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t b_addr = s32(sB + (size_t)b * T4_SB_BYTES);
+                for (uint32_t m = 0; m < n_mtiles; m++, ia++) {
+                    const uint32_t s = ia % T4_A_STAGES;
+                    bar_wait(&a_full[s], (ia / T4_A_STAGES) & 1u);
+                    const uint32_t a_addr = s32(sA + (size_t)s * T4_A_BYTES);
+#pragma unroll
+                    for (uint32_t t = 0; t < T4_NB; t++, id++) {
+                        const uint32_t acc = id & 1u;
+                        bar_wait(&d_empty[acc], ((id >> 1) & 1u) ^ 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t d_addr = tmem + acc * T4_N;
+#pragma unroll
+                        for (uint32_t k = 0; k < 4; k++) {
+                            const uint64_t da = smem_desc(a_addr + k * 2 * T4_LBO);
+                            const uint64_t db = smem_desc(b_addr + t * T4_B_BYTES + k * 2 * T4_LBO);
+                            const uint32_t accumulate = k > 0 ? 1u : 0u;
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t"
+                                "setp.ne.b32 p, %4, 0;\n\t"
+                                "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}" ::
+                                    "r"(d_addr),
+                                "l"(da), "l"(db), "r"(T4_IDESC), "r"(accumulate), "r"(tmem + T4_SF_COL), "r"(tmem + T4_SF_COL + 16)
+                                : "memory");
+                        }
+                        umma_commit(&d_full[acc]);    // accumulator ready for the epilogue
+                    }
+                    umma_commit(&a_empty[s]);         // A stage may be refilled once these MMAs retire
+                }
+                umma_commit(&b_empty[b]);             // B buffer may be overwritten
+            }
+        }
+    } else if (warp < 4) {
+        // ===== B expanders: 64 threads, thread t expands rows t, t+64, ... of the super-tile, 4 rows at a time =====
+        const uint32_t t = threadIdx.x - 64;
+        uint32_t i = 0;
+        for (uint64_t st = blockIdx.x; st < n_stiles; st += gridDim.x, i++) {
+            const uint32_t b = i & 1u;
+            uint8_t *buf = sB + (size_t)b * T4_SB_BYTES;
+#pragma unroll 1
+            for (uint32_t g = 0; g < 2; g++) {
+                uint4 lo[4], hi[4];
+#pragma unroll
+                for (uint32_t h = 0; h < 4; h++) {  // loads first: the HBM latency overlaps the wait for the buffer
+                    const uint32_t r = t + T4_EXP_THREADS * (4 * g + h);
+                    const uint64_t row = st * T4_ROWS + r;
+                    lo[h] = make_uint4(0, 0, 0, 0);
+                    hi[h] = lo[h];
+                    if (r < T4_ROWS && row < n_rows) {
+                        lo[h] = __ldg(rows + 2 * row);
+                        hi[h] = __ldg(rows + 2 * row + 1);
+                    }
+                }
+                if (g == 0)
+                    bar_wait(&b_empty[b], ((i >> 1) & 1u) ^ 1u);
+#pragma unroll
+                for (uint32_t h = 0; h < 4; h++) {
+                    const uint32_t r = t + T4_EXP_THREADS * (4 * g + h);
+                    if (r < T4_ROWS) {
+                        uint8_t *tile = buf + (r / T4_N) * T4_B_BYTES;
+                        const uint32_t rr = r % T4_N;
+                        const uint32_t w[8] = {lo[h].x, lo[h].y, lo[h].z, lo[h].w, hi[h].x, hi[h].y, hi[h].z, hi[h].w};
+#pragma unroll
+                        for (uint32_t kc = 0; kc < 8; kc++)
+                            *reinterpret_cast<uint4 *>(tile + tile_off(rr, kc)) = expand32(w[kc]);
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
+            bar_arrive(&b_full[b]);
+        }
+    } else {
+        // ===== epilogue: TMEM lane quadrant = warp % 4, column half = (warp - 4) / 4 =====
+        const uint32_t quad = warp & 3u, half = (uint32_t)(warp - 4) >> 2;
+        const uint32_t lane_base = tmem + ((quad * 32u) << 16) + half * T4_EW;
+        const uint64_t my_tiles = blockIdx.x < n_stiles ? (n_stiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const uint64_t total = my_tiles * n_mtiles * T4_NB;   // accumulator tiles this CTA produces
+        int32_t va[T4_EB], vb[T4_EB];
+        uint64_t st = blockIdx.x;
+        uint32_t m = 0, t = 0;
+        if (total > 0) {
+            bar_wait(&d_full[0], 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            load_batch(va, lane_base);
+        }
+        for (uint64_t id = 0; id < total; id++) {
+            const uint32_t acc = (uint32_t)id & 1u;
+            const uint32_t needle = m * T4_M + quad * 32 + lane;
+            const uint64_t row0 = st * T4_ROWS + t * T4_N + half * T4_EW;
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            load_batch(vb, lane_base + acc * T4_N + T4_EB);
+            process_batch(va, min_bits, row0, n_rows, needle, q, sink);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0)
+                bar_arrive(&d_empty[acc]);     // every TMEM read of this accumulator has completed
+            const bool more = id + 1 < total;
+            const uint32_t nacc = acc ^ 1u, npar = (uint32_t)((id + 1) >> 1) & 1u;
+            bool issued = false;
+            if (more && bar_try(&d_full[nacc], npar)) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                load_batch(va, lane_base + nacc * T4_N);
+                issued = true;
+            }
+            process_batch(vb, min_bits, row0 + T4_EB, n_rows, needle, q, sink);
+            if (more && !issued) {
+                bar_wait(&d_full[nacc], npar);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                load_batch(va, lane_base + nacc * T4_N);
+            }
+            // advance (t fastest, then m, then super-tile) -- the MMA issue order
+            if (++t == T4_NB) {
+                t = 0;
+                if (++m == n_mtiles) {
+                    m = 0;
+                    st += gridDim.x;
+                }
+            }
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+}  // namespace
+
+int launch_match_tensor4(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles, size_t q,
+                         uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
+                         unsigned long long *min_key, int mode, int sm_count, cudaStream_t s)
+{
+    if (n_rows == 0 || q == 0)
+        return 0;
+    if (threshold > 127)       // the raw-bit compare of the epilogue needs dot_min = 256 - 2 thr > 0
+        return YUME_PDQ_CUDA_E_INVALID;
+    const uint32_t n_mtiles = (uint32_t)((q + T4_M - 1) / T4_M);
+    uint8_t *exp = nullptr;
+    cudaError_t e = cudaMallocAsync(&exp, (size_t)n_mtiles * T4_A_BYTES, s);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? YUME_PDQ_CUDA_E_NOMEM : (int)e;
+    }
+    const uint32_t threads = n_mtiles * T4_M * 2;
+    expand_needles4_kernel<<<(threads + 255) / 256, 256, 0, s>>>(reinterpret_cast<const uint4 *>(needles), (uint32_t)q, exp,
+                                                                 n_mtiles);
+    YPDQ_LAUNCH_CHECK();
+    static bool attr_set = false;
+    if (!attr_set) {
+        YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM));
+        attr_set = true;
+    }
+    Tc4Sink sink{out, cap, count, min_key, row_offset, (uint64_t)q, mode};
+    const uint64_t n_stiles = (n_rows + T4_ROWS - 1) / T4_ROWS;
+    const unsigned grid = (unsigned)std::min<uint64_t>(n_stiles, (uint64_t)sm_count);
+    const float dot_min = (float)(256 - 2 * (int32_t)threshold);
+    int32_t min_bits;
+    memcpy(&min_bits, &dot_min, 4);
+    match_tensor4_kernel<<<grid, T4_THREADS, T4_SMEM, s>>>(reinterpret_cast<const uint4 *>(rows), n_rows, exp, n_mtiles,
+                                                           (uint32_t)q, min_bits, sink);
+    YPDQ_LAUNCH_CHECK();
+    YPDQ_CUDA_TRY(cudaFreeAsync(exp, s));
+    return 0;
+}
+
+}  // namespace ypdq
