@@ -345,10 +345,10 @@ def main():
         torch.cuda.synchronize()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
         if flush is not None:
-            flush.zero_()
+            flush.sum()
         for a, b in ev:
             if flush is not None:
-                flush.zero_()
+                flush.sum()   # READ 256 MB: evicts L2 without leaving dirty lines to write back under the timed kernel
             a.record()
             fn()
             b.record()
@@ -358,14 +358,12 @@ def main():
 
     line_extra = {}
     if rank == 0:
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
         nd = outs["hashes"].reshape(-1, 32)
-        # (1) dominant kernel of the step: large-batch match (INT/XU-pipe bound)
+        # (1) dominant kernel of the step: large-batch match on the tensor cores
         m_mean, m_med, _ = time_kernel(
             lambda: (match_cnt.zero_(), matcher.find_device(nd, B * 8, match_out, CAP, match_cnt)), 3)
         pairs = shard_rows * B * 8
-        sm_mhz = clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
-        xu_peak = 148 * 16 * sm_mhz * 1e6 / 2 / 1e12      # Tpairs/s at 2 POPC per pair, 16 POPC/clk/SM
         # (2) hash kernel (HBM bound): algorithmic bytes = frames in + hashes/quality/thresholds out
         h_mean, h_med, h_min = time_kernel(lambda: kern.hash_batch(frames, out=outs), 10, flush)
         hash_bytes = B * (512 * 512 * 4 + 8 * 32 + 8 * 4 + 8 * 4)
@@ -375,13 +373,21 @@ def main():
             lambda: matcher.find_device(n8, 8, match_out, CAP, match_cnt), 20, flush)
         scan_bytes = shard_rows * 32
         share = m_mean / (m_mean + h_mean)
+        # Tensor roofline: one (row, needle) pair = 256 multiply-adds = 512 ops of the packed-FP4 MMA
+        # (tcgen05.mma kind::mxf4, e2m1 +-1 operands, f32 accumulate).  MEASURED_PEAKS.json holds the dense
+        # bf16 rate; the FP4 pipe is 4x the bf16 pipe (9 vs 2.25 PFLOP/s nominal), so peak = 4 x the bf16
+        # figure (the sustained one: this kernel is timed inside a long step).
+        bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+        tensor_peak = 4.0 * bf16
+        achieved_tops = pairs * 512 / (m_mean * 1e-3) / 1e12
         line_extra["roofline"] = {
-            "kernel": "match_tiled_kernel (needle batch 32768 x this rank's DB shard)",
-            "bound": "int",
-            "achieved": pairs / (m_mean * 1e-3) / 1e12, "peak": xu_peak, "unit": "Tpairs/s",
-            "frac": pairs / (m_mean * 1e-3) / 1e12 / xu_peak,
-            "peak_source": ("POPC (XU) pipe: 148 SMs x 16 POPC/clk x median SM clock under load / 2 POPC per "
-                            "pair; no entry for an integer pipe exists in MEASURED_PEAKS.json"),
+            "kernel": "match_tensor4_kernel (tcgen05.mma kind::mxf4; needle batch %d x this rank's %d-row shard)"
+                      % (B * 8, shard_rows),
+            "bound": "tensor", "achieved": achieved_tops, "peak": tensor_peak, "unit": "TFLOP/s",
+            "frac": achieved_tops / tensor_peak,
+            "peak_source": ("4 x bf16_tflops_sustained of MEASURED_PEAKS.json (FP4 : bf16 = 4 : 1 on the tensor "
+                            "pipe); raw mxf4 issue rate measured on this pool by tools/mma_peak.cu: 8900 TFLOP/s"),
+            "tpairs_per_s": pairs / (m_mean * 1e-3) / 1e12,
             "traffic": None, "ms_per_launch": m_mean, "share_of_step": share,
         }
         line_extra["roofline_hash"] = {
@@ -409,14 +415,14 @@ def main():
         hk = yp.CudaKernel(local_rank)
 
         def e2e_step():
+            if n_gpus == 1:
+                # one pipelined C-ABI call: H2D of chunk i+1 overlaps hash + match of chunk i
+                return matcher.screen(host_frames.numpy(), hashes=host_hashes)
             hk.hash_batch(host_frames.numpy(), want_quality=False, want_thresholds=False,
                           out={"hashes": host_hashes})
-            needles = host_hashes.reshape(-1, 32)
-            if n_gpus > 1:
-                nt = torch.from_numpy(needles).to(dev)
-                dist.all_gather_into_tensor(needles_all, nt)
-                return matcher.find_all(needles_all)
-            return matcher.find_all(needles)
+            nt = torch.from_numpy(host_hashes.reshape(-1, 32)).to(dev)
+            dist.all_gather_into_tensor(needles_all, nt)
+            return matcher.find_all(needles_all)
 
         e2e_step()
         barrier()
@@ -433,7 +439,9 @@ def main():
                "h2d_bytes_per_step": int(B * 512 * 512 * 4 + B * 8 * 32),
                "d2h_bytes_per_step": int(B * 8 * 32 + 16 + len(m) * 16),
                "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
-               "path": "yume_pdq_cuda_hash_batch(host frames) + yume_pdq_cuda_matcher_find(host needles)"}
+               "path": ("yume_pdq_cuda_screen_batch(pinned host frames -> host hashes + sorted host match list)"
+                        if n_gpus == 1 else
+                        "yume_pdq_cuda_hash_batch(host frames) + NCCL all-gather + yume_pdq_cuda_matcher_find")}
         del host_frames
 
     cpu_bl = None
@@ -444,7 +452,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (hash) / u32 popcount (match)",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (hash) / e2m1 x e2m1 -> f32 exact (match, tensor cores) / u32 popcount (8-needle scan)",
             "data": "synthetic", "config": workload_config(n_gpus),
             "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks,
             "matches_per_step": n_matches, "planted": N_PLANT,

@@ -205,6 +205,17 @@ int yume_pdq_cuda_matcher_find_device(YumePDQ_CudaDb *db, const uint8_t *needles
                                       uint32_t threshold, YumePDQ_Match *out_dev, uint32_t cap,
                                       uint32_t *count_dev, int algo, void *stream);
 
+/* Hash + match in one pipelined call: the flow of examples/end_to_end.rs:224-256 (hash_get_threshold ->
+ * visit_dihedrals -> matcher.find for every frame) for a whole batch.  frames n x 512 x 512 f32, host or
+ * device; host frames are copied in 128-frame chunks and chunk i's hash + match kernels overlap the copy
+ * of chunk i+1.  Needle index of a match = 8 * frame + dihedral (YUME_PDQ_CUDA_DIHEDRAL_ORDER).
+ * hashes (n x 8 x 32, nullable) and quality (n x 8, nullable) may be host or device; out (host, cap
+ * entries) receives the matches sorted by (row, needle) exactly like yume_pdq_cuda_matcher_find;
+ * *n_found the total; YUME_PDQ_CUDA_E_CAPACITY if it exceeds cap.  This is what bench.py's e2e leg times. */
+int yume_pdq_cuda_screen_batch(YumePDQ_CudaDb *db, const float *frames, size_t n, uint32_t threshold,
+                               uint8_t *hashes, float *quality, YumePDQ_Match *out, size_t cap,
+                               size_t *n_found, void *stream);
+
 /* ---- synthetic inputs (device-side generators shared with the oracle) ----
  * frames_dev n x 512 x 512 f32 DEVICE pointer. kind 0: uniform 8-bit noise;
  * kind 1: smooth integer triangle waves + noise (see oracle/pdq_oracle.c). */

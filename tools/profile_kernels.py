@@ -1,5 +1,5 @@
 """Short driver for ncu captures: launches each hot kernel a few times at profile-friendly sizes.
-usage: python tools/profile_kernels.py [hash] [scan] [stream] [tiled] [exact]"""
+usage: python tools/profile_kernels.py [hash] [scan] [stream] [tiled] [exact] [tensor]"""
 import os
 import sys
 
@@ -23,7 +23,7 @@ if "hash" in what:
     for _ in range(3):
         k.hash_batch(frames, out=outs)
     torch.cuda.synchronize()
-if {"scan", "stream", "tiled", "exact"} & set(what):
+if {"scan", "stream", "tiled", "exact", "tensor"} & set(what):
     n = (10_000_000 // 2048 + 1) * 2048
     db = yp.CudaVectorDatabase(synthetic_rows=n)
     m = yp.CudaMatcher(db, 31)
@@ -31,6 +31,7 @@ if {"scan", "stream", "tiled", "exact"} & set(what):
     cnt = torch.zeros(1, dtype=torch.int32, device=dev)
     n8 = torch.from_numpy(rng.integers(0, 256, size=(8, 32), dtype=np.uint8)).cuda()
     nbig = torch.from_numpy(rng.integers(0, 256, size=(2048, 32), dtype=np.uint8)).cuda()
+    nbig4 = torch.from_numpy(rng.integers(0, 256, size=(4096, 32), dtype=np.uint8)).cuda()
     for _ in range(3):
         if "scan" in what:
             m.find_device(n8, 8, out, 1 << 16, cnt, algo=yp.ALGO_TILED)
@@ -40,5 +41,7 @@ if {"scan", "stream", "tiled", "exact"} & set(what):
             m.find_device(n8, 8, out, 1 << 16, cnt, algo=yp.ALGO_EXACT)
         if "tiled" in what:
             m.find_device(nbig, 2048, out, 1 << 16, cnt, algo=yp.ALGO_TILED)
+        if "tensor" in what:
+            m.find_device(nbig4, 4096, out, 1 << 16, cnt, algo=yp.ALGO_TENSOR)
     torch.cuda.synchronize()
 print("done")

@@ -11,21 +11,21 @@ import yume_pdq_b200 as yp
 
 
 def timeit(fn, iters=20, warm=3, flush=None):
+    """median / best in microseconds; everything is enqueued asynchronously so no host launch gap is timed"""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
-    ts = []
-    for _ in range(iters):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    if flush is not None:
+        flush.sum()
+    for e0, e1 in ev:
         if flush is not None:
-            flush.zero_()
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
+            flush.sum()      # READ 256 MB: evicts L2 without leaving dirty lines to write back during the timed kernel
         e0.record()
         fn()
         e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1) * 1e3)
-    ts.sort()
+    torch.cuda.synchronize()
+    ts = sorted(e0.elapsed_time(e1) * 1e3 for e0, e1 in ev)
     return ts[len(ts) // 2], ts[0]
 
 
@@ -33,7 +33,7 @@ def main():
     what = sys.argv[1:] or ["scan", "hash", "tiled"]
     torch.cuda.init()
     print(torch.cuda.get_device_name(0))
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    flush = torch.zeros(64 << 20, dtype=torch.float32, device="cuda")   # 256 MB
     rng = np.random.default_rng(0)
     if "scan" in what:
         n = (10_000_000 // 2048 + 1) * 2048
@@ -48,6 +48,20 @@ def main():
                 print(f"scan 10M x {q:3d} {name:7s}: median {med:8.1f} us  best {best:8.1f} us  "
                       f"{n * 32 / med / 1e3:7.1f} GB/s  {n * q / med / 1e6:8.3f} Tpairs/s  hits={int(cnt.item())}")
                 cnt.zero_()
+        db.close()
+    if "scanv" in what:   # tiled-kernel variants (YPDQ_TILED_VARIANT, one process per variant)
+        n = (10_000_000 // 2048 + 1) * 2048
+        db = yp.CudaVectorDatabase(synthetic_rows=n)
+        m = yp.CudaMatcher(db, 31)
+        out = torch.zeros((1 << 16, 16), dtype=torch.uint8, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for q in (8, 16, 64, 256):
+            needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
+            med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 16, cnt, algo=yp.ALGO_TILED), flush=flush)
+            med2, best2 = timeit(lambda: m.find_device(needles, q, out, 1 << 16, cnt, algo=yp.ALGO_TILED), flush=None)
+            print(f"variant {os.environ.get('YPDQ_TILED_VARIANT', '-')}: scan 10M x {q:3d}: median {med:8.1f} us  "
+                  f"best {best:8.1f} us  {n * 32 / med / 1e3:7.1f} GB/s  {n * q / med / 1e6:8.3f} Tpairs/s   "
+                  f"[back-to-back, no flush: median {med2:8.1f} us best {best2:8.1f}]")
         db.close()
     if "tiled" in what:
         n = (10_000_000 // 2048 + 1) * 2048

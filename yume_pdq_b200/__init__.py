@@ -94,6 +94,8 @@ SIGNATURES = {
                                                  C.POINTER(C.c_uint64), _vp]),
     "yume_pdq_cuda_matcher_find_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _vp, C.c_uint32,
                                                     _vp, C.c_int, _vp]),
+    "yume_pdq_cuda_screen_batch": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _vp, _vp, _vp, C.c_size_t,
+                                             C.POINTER(C.c_size_t), _vp]),
     "yume_pdq_cuda_synth_frames": (C.c_int, [C.c_int, _vp, C.c_size_t, C.c_uint64, C.c_uint64, C.c_int, _vp]),
     "yume_pdq_cuda_synth_rows": (C.c_int, [C.c_int, _vp, C.c_size_t, C.c_uint64, C.c_uint64, _vp]),
 }
@@ -463,6 +465,24 @@ class CudaMatcher:
         if k.value == 0xFFFFFFFFFFFFFFFF:
             return None
         return int(k.value) // q, int(k.value) % q
+
+    def screen(self, frames, hashes=None, quality=None, cap: int = 65536):
+        """Hash ``frames`` (n x 512 x 512 f32, numpy or torch CUDA) and match all 8 n dihedral hashes
+        against the haystack in one pipelined call (examples/end_to_end.rs:224-256 for a batch).
+        Returns the matches (needle = 8 * frame + dihedral) sorted by (row, needle); fills ``hashes``
+        (n x 8 x 32) / ``quality`` (n x 8) when given."""
+        n = int(frames.shape[0])
+        while True:
+            out = np.zeros(max(cap, 1), dtype=MATCH_DTYPE)
+            k = C.c_size_t(0)
+            rc = lib.yume_pdq_cuda_screen_batch(self.haystack._h, _ptr(frames), n, self.threshold,
+                                                _ptr(hashes), _ptr(quality), _ptr(out), cap, C.byref(k),
+                                                _stream(self.stream))
+            if rc == E_CAPACITY:
+                cap = int(k.value)
+                continue
+            _check(rc, "screen_batch")
+            return out[: k.value].copy()
 
     def find_device(self, needles_dev, q: int, out_dev, cap: int, count_dev, algo: int = ALGO_AUTO,
                     stream=None):

@@ -313,47 +313,24 @@ const char *yume_pdq_cuda_kernel_ident(void) { return "cuda_sm100a_f32_bitexact_
 const char *yume_pdq_cuda_matcher_ident(void) { return "CudaMatcher (sm_100a, carry-save prefilter + popc)"; }
 uint64_t yume_pdq_cuda_launch_count(void) { return g_launches.load(); }
 
-int yume_pdq_cuda_hash_batch(int device, const float *frames, size_t n, uint8_t *hashes,
-                             float *quality, float *thresholds, float *pdqf, void *stream)
+}  // extern "C"
+
+namespace {
+
+// Hashes n frames into DEVICE output buffers on stream s.  Device-resident frames: one launch.  Host frames:
+// double-buffered chunks of `chunk` frames, the H2D copy of chunk i+1 (copy stream) overlaps the kernels of
+// chunk i.  after_chunk(first_frame, count) is invoked (host side, work enqueued on s) once the hash
+// kernel of each chunk has been enqueued -- yume_pdq_cuda_screen_batch enqueues that chunk's match there.
+// d_in: device scratch for 2 * chunk frames (host frames only).
+template <class F>
+int hash_chunks(int device, const float *frames, size_t n, uint8_t *d_hashes, float *d_quality, float *d_thr,
+                float *d_pdqf, cudaStream_t s, size_t chunk, float *d_in0, F after_chunk)
 {
-    if (!frames || !hashes)
-        return n == 0 ? 0 : YUME_PDQ_CUDA_E_INVALID;
-    if (n == 0)
-        return 0;
-    int rc = ensure_device(device);
-    if (rc)
-        return rc;
-    cudaStream_t s = (cudaStream_t)stream;
-    const bool frames_on_host = !is_device_ptr(frames);
-    // outputs: staged through one scratch block when they live on the host
-    Scratch &so = tls_scratch(0);
-    size_t out_need = host_bytes(hashes, n * 256) + host_bytes(quality, n * 32) +
-                      host_bytes(thresholds, n * 32) + host_bytes(pdqf, n * 1024);
-    // frames on the host: double-buffered chunks so the H2D copy of chunk i+1 overlaps
-    // the kernel of chunk i
-    const size_t CH = 64;  // frames per chunk (64 MiB)
-    const size_t chunk = std::min(n, CH);
-    size_t in_need = frames_on_host ? 2 * chunk * (size_t)(512 * 512 * 4) : 0;
-    rc = so.reserve(device, out_need + in_need + 4096, 0);
-    if (rc)
-        return rc;
-    Stager st(s);
-    st.base = reinterpret_cast<uint8_t *>(so.dev);
-    uint8_t *d_hashes;
-    float *d_quality, *d_thr, *d_pdqf;
-    st.out(hashes, n * 256, &d_hashes);
-    st.out(quality, n * 32, &d_quality);
-    st.out(thresholds, n * 32, &d_thr);
-    st.out(pdqf, n * 1024, &d_pdqf);
-    if (!frames_on_host) {
-        rc = launch_hash_batch(frames, n, d_hashes, d_quality, d_thr, d_pdqf, s);
-        if (rc)
-            return rc;
-        return st.finish();
+    if (is_device_ptr(frames)) {
+        int rc = launch_hash_batch(frames, n, d_hashes, d_quality, d_thr, d_pdqf, s);
+        return rc ? rc : after_chunk((size_t)0, n);
     }
-    float *d_in[2];
-    d_in[0] = reinterpret_cast<float *>(st.base + align_up(st.off, 256));
-    d_in[1] = d_in[0] + chunk * (512 * 512);
+    float *d_in[2] = {d_in0, d_in0 + chunk * (512 * 512)};
     static thread_local cudaStream_t copy_stream = nullptr;
     static thread_local cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     static thread_local int ev_dev = -1;
@@ -378,16 +355,61 @@ int yume_pdq_cuda_hash_batch(int device, const float *frames, size_t n, uint8_t 
                                       cudaMemcpyHostToDevice, copy_stream));
         YPDQ_CUDA_TRY(cudaEventRecord(ev_copied[b], copy_stream));
         YPDQ_CUDA_TRY(cudaStreamWaitEvent(s, ev_copied[b], 0));
-        rc = launch_hash_batch(d_in[b], cnt, d_hashes + f0 * 256, d_quality ? d_quality + f0 * 8 : nullptr,
-                               d_thr ? d_thr + f0 * 8 : nullptr, d_pdqf ? d_pdqf + f0 * 256 : nullptr, s);
+        int rc = launch_hash_batch(d_in[b], cnt, d_hashes + f0 * 256, d_quality ? d_quality + f0 * 8 : nullptr,
+                                   d_thr ? d_thr + f0 * 8 : nullptr, d_pdqf ? d_pdqf + f0 * 256 : nullptr, s);
         if (rc)
             return rc;
-        YPDQ_CUDA_TRY(cudaEventRecord(ev_done[b], s));
+        YPDQ_CUDA_TRY(cudaEventRecord(ev_done[b], s));   // the frame buffer is free once the hash kernel ran
+        rc = after_chunk(f0, cnt);
+        if (rc)
+            return rc;
     }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int yume_pdq_cuda_hash_batch(int device, const float *frames, size_t n, uint8_t *hashes,
+                             float *quality, float *thresholds, float *pdqf, void *stream)
+{
+    if (!frames || !hashes)
+        return n == 0 ? 0 : YUME_PDQ_CUDA_E_INVALID;
+    if (n == 0)
+        return 0;
+    int rc = ensure_device(device);
+    if (rc)
+        return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool frames_on_host = !is_device_ptr(frames);
+    // outputs: staged through one scratch block when they live on the host
+    Scratch &so = tls_scratch(0);
+    size_t out_need = host_bytes(hashes, n * 256) + host_bytes(quality, n * 32) +
+                      host_bytes(thresholds, n * 32) + host_bytes(pdqf, n * 1024);
+    const size_t chunk = std::min<size_t>(n, 64);  // frames per H2D chunk (64 MiB)
+    size_t in_need = frames_on_host ? 2 * chunk * (size_t)(512 * 512 * 4) : 0;
+    rc = so.reserve(device, out_need + in_need + 4096, 0);
+    if (rc)
+        return rc;
+    Stager st(s);
+    st.base = reinterpret_cast<uint8_t *>(so.dev);
+    uint8_t *d_hashes;
+    float *d_quality, *d_thr, *d_pdqf;
+    st.out(hashes, n * 256, &d_hashes);
+    st.out(quality, n * 32, &d_quality);
+    st.out(thresholds, n * 32, &d_thr);
+    st.out(pdqf, n * 1024, &d_pdqf);
+    float *d_in = reinterpret_cast<float *>(st.base + align_up(st.off, 256));
+    rc = hash_chunks(device, frames, n, d_hashes, d_quality, d_thr, d_pdqf, s, chunk, d_in,
+                     [](size_t, size_t) { return 0; });
+    if (rc)
+        return rc;
     rc = st.finish();
     if (rc)
         return rc;
-    YPDQ_CUDA_TRY(cudaStreamSynchronize(s));
+    if (frames_on_host)
+        YPDQ_CUDA_TRY(cudaStreamSynchronize(s));
     return 0;
 }
 
@@ -774,6 +796,105 @@ int yume_pdq_cuda_matcher_find_device(YumePDQ_CudaDb *db, const uint8_t *needles
         return rc;
     return launch_match(db->rows, db->n_rows, db->offset, needles_dev, q, threshold, out_dev, cap,
                         count_dev, nullptr, MODE_LIST, algo, db->sm_count, (cudaStream_t)stream);
+}
+
+int yume_pdq_cuda_screen_batch(YumePDQ_CudaDb *db, const float *frames, size_t n, uint32_t threshold,
+                               uint8_t *hashes, float *quality, YumePDQ_Match *out, size_t cap,
+                               size_t *n_found, void *stream)
+{
+    if (!db || !n_found || (cap && !out) || (n && !frames) || n > 0x1fffffffull)
+        return YUME_PDQ_CUDA_E_INVALID;
+    *n_found = 0;
+    if (n == 0)
+        return 0;
+    int rc = ensure_device(db->device);
+    if (rc)
+        return rc;
+    std::lock_guard<std::mutex> lock(db->mu);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int device = db->device;
+    const bool frames_on_host = !is_device_ptr(frames);
+    // device staging: hashes always (they are the needles), quality if wanted on the host, frame chunks
+    const size_t chunk = std::min<size_t>(n, 128);   // frames per pipeline step: 128 MiB H2D, 1024 needles
+    Scratch &so = tls_scratch(1);
+    const bool hashes_dev = hashes && is_device_ptr(hashes);
+    const size_t need = (hashes_dev ? 0 : align_up(n * 256, 256)) + host_bytes(quality, n * 32) +
+                        (frames_on_host ? 2 * chunk * (size_t)(512 * 512 * 4) : 0) + 4096;
+    rc = so.reserve(device, need, 0);
+    if (rc)
+        return rc;
+    uint8_t *base = reinterpret_cast<uint8_t *>(so.dev);
+    size_t off = 0;
+    uint8_t *d_hashes = hashes_dev ? hashes : base;
+    if (!hashes_dev)
+        off += align_up(n * 256, 256);
+    float *d_quality = quality;
+    if (quality && !is_device_ptr(quality)) {
+        d_quality = reinterpret_cast<float *>(base + off);
+        off += align_up(n * 32, 256);
+    }
+    float *d_in = reinterpret_cast<float *>(base + off);
+
+    size_t list_cap = std::max<size_t>(cap, 1 << 16);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (db->out_cap < list_cap) {
+            if (db->d_out) cudaFree(db->d_out);
+            db->d_out = nullptr;
+            db->out_cap = 0;
+            if (cudaMalloc(&db->d_out, list_cap * sizeof(YumePDQ_Match)) != cudaSuccess) {
+                (void)cudaGetLastError();
+                return YUME_PDQ_CUDA_E_NOMEM;
+            }
+            db->out_cap = list_cap;
+        }
+        const uint32_t dev_cap = (uint32_t)std::min<size_t>(db->out_cap, 0xffffffffu);
+        struct Init {
+            uint32_t count, pad;
+            unsigned long long min;
+        } init = {0, 0, ~0ull};
+        std::memcpy(db->h_pin, &init, 16);
+        YPDQ_CUDA_TRY(cudaMemcpyAsync(db->d_count, db->h_pin, 16, cudaMemcpyHostToDevice, s));
+        auto match_chunk = [&](size_t f0, size_t cnt) -> int {
+            return launch_match(db->rows, db->n_rows, db->offset, d_hashes + f0 * 256, cnt * 8, threshold, db->d_out,
+                                dev_cap, db->d_count, db->d_min, MODE_LIST, YUME_PDQ_CUDA_ALGO_AUTO, db->sm_count, s,
+                                (uint32_t)(f0 * 8));
+        };
+        if (attempt == 0) {
+            // pipeline: [H2D chunk i+1] || [hash chunk i -> match chunk i's 8 * cnt needles]
+            rc = hash_chunks(device, frames, n, d_hashes, d_quality, nullptr, nullptr, s, chunk, d_in, match_chunk);
+        } else {
+            rc = match_chunk(0, n);   // list overflow: the hashes are resident, rescan with a larger list
+        }
+        if (rc)
+            return rc;
+        YPDQ_CUDA_TRY(cudaMemcpyAsync(db->h_pin, db->d_count, 16, cudaMemcpyDeviceToHost, s));
+        if (attempt == 0) {
+            if (hashes && !hashes_dev)
+                YPDQ_CUDA_TRY(cudaMemcpyAsync(hashes, d_hashes, n * 256, cudaMemcpyDeviceToHost, s));
+            if (quality && d_quality != quality)
+                YPDQ_CUDA_TRY(cudaMemcpyAsync(quality, d_quality, n * 32, cudaMemcpyDeviceToHost, s));
+        }
+        YPDQ_CUDA_TRY(cudaStreamSynchronize(s));
+        Init res;
+        std::memcpy(&res, db->h_pin, 16);
+        *n_found = res.count;
+        if (res.count > dev_cap && attempt == 0) {
+            list_cap = res.count;   // the sorted prefix must be exact: grow and rescan
+            continue;
+        }
+        std::vector<YumePDQ_Match> hits(std::min<size_t>(res.count, dev_cap));
+        if (!hits.empty())
+            YPDQ_CUDA_TRY(cudaMemcpy(hits.data(), db->d_out, hits.size() * sizeof(YumePDQ_Match),
+                                     cudaMemcpyDeviceToHost));
+        std::sort(hits.begin(), hits.end(), [](const YumePDQ_Match &a, const YumePDQ_Match &b) {
+            return a.row != b.row ? a.row < b.row : a.needle < b.needle;
+        });
+        const size_t k = std::min(cap, hits.size());
+        if (k)
+            std::memcpy(out, hits.data(), k * sizeof(YumePDQ_Match));
+        return res.count > cap ? YUME_PDQ_CUDA_E_CAPACITY : 0;
+    }
+    return YUME_PDQ_CUDA_E_CAPACITY;
 }
 
 int yume_pdq_cuda_synth_frames(int device, float *frames_dev, size_t n, uint64_t first_frame, uint64_t seed,

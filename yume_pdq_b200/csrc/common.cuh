@@ -59,15 +59,16 @@ int launch_dihedrals(const float *pdqf, const float *thr0, size_t n, uint8_t *ha
 enum MatchMode : int { MODE_LIST = 0, MODE_MIN = 1 };
 int launch_match(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
                  size_t q, uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
-                 unsigned long long *min_key, int mode, int algo, int sm_count, cudaStream_t s);
+                 unsigned long long *min_key, int mode, int algo, int sm_count, cudaStream_t s,
+                 uint32_t needle_base = 0);
 
 int launch_match_tensor(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
                         size_t q, uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
-                        unsigned long long *min_key, int mode, int sm_count, cudaStream_t s);
+                        unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base = 0);
 
 int launch_match_tensor4(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
                          size_t q, uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
-                         unsigned long long *min_key, int mode, int sm_count, cudaStream_t s);
+                         unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base = 0);
 
 int launch_synth_frames(float *frames, size_t n, uint64_t first, uint64_t seed, int kind,
                         cudaStream_t s);

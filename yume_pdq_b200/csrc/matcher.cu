@@ -29,6 +29,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ypdq {
@@ -76,6 +78,7 @@ struct Sink {
     uint64_t row_offset;
     uint64_t q;
     int mode;
+    uint32_t needle_base;   // added to reported needle indices (LIST mode): pipelined callers match in chunks
 };
 
 // one hit from divergent code
@@ -88,7 +91,7 @@ __device__ __forceinline__ void emit_single(const Sink &k, uint64_t local_row, u
     } else if (pos < k.cap) {
         YumePDQ_Match m;
         m.row = local_row + k.row_offset;
-        m.needle = needle;
+        m.needle = needle + k.needle_base;
         m.dist = dist;
         k.out[pos] = m;
     }
@@ -116,7 +119,7 @@ __device__ __forceinline__ void emit_ballot(const Sink &k, bool hit, uint64_t lo
             if (pos < k.cap) {
                 YumePDQ_Match m;
                 m.row = local_row + k.row_offset;
-                m.needle = needle;
+                m.needle = needle + k.needle_base;
                 m.dist = dist;
                 k.out[pos] = m;
             }
@@ -162,18 +165,23 @@ match_exact_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint4 
 
 // ------------------------------------------------------------ ALGO_TILED --
 constexpr int TL_THREADS = 256;
-constexpr int TL_ROWS = 8;        // rows per thread held in registers
 constexpr int TL_NCHUNK = 2048;   // needles per CTA
 constexpr int TL_SUB = 1024;      // needles between candidate-queue drains
 constexpr int TL_QCAP = 2048;     // candidate queue entries
+constexpr int TL_DEFAULT_VARIANT = 3;  // 4 rows/thread, 6 CTAs/SM: fastest measured for q = 8 .. 256 (profiles/r01_scan_variants.log)
 
-__global__ void __launch_bounds__(TL_THREADS)
+template <int TL_ROWS, int MINB>   // rows per thread held in registers, min resident CTAs per SM
+__global__ void __launch_bounds__(TL_THREADS, MINB)
 match_tiled_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint4 *__restrict__ needles,
                    uint32_t q, uint32_t thr, Sink sink)
 {
-    __shared__ uint4 spre[TL_NCHUNK];      // {n0^n1^n2, n0, n1, n3}
-    __shared__ uint32_t squeue[TL_QCAP];   // (local row << 11) | local needle
+    // dynamic shared memory sized by the launcher to the needle chunk actually present, so that small
+    // batches leave room for many resident CTAs
+    extern __shared__ uint4 tl_smem[];
     __shared__ uint32_t sqcount;
+    const uint32_t n_alloc = min((uint32_t)TL_NCHUNK, q);
+    uint4 *spre = tl_smem;                                             // {n0^n1^n2, n0, n1, n3}
+    uint32_t *squeue = reinterpret_cast<uint32_t *>(tl_smem + n_alloc);  // (local row << 11) | local needle
     const uint32_t n_first = blockIdx.y * TL_NCHUNK;
     const uint32_t nc = min((uint32_t)TL_NCHUNK, q - n_first);
     for (uint32_t i = threadIdx.x; i < nc; i += TL_THREADS) {
@@ -406,13 +414,14 @@ match_stream_kernel(const uint8_t *__restrict__ rows, uint64_t n_rows,
 // --------------------------------------------------------------- launcher --
 int launch_match(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
                  size_t q, uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
-                 unsigned long long *min_key, int mode, int algo, int sm_count, cudaStream_t s)
+                 unsigned long long *min_key, int mode, int algo, int sm_count, cudaStream_t s,
+                 uint32_t needle_base)
 {
     if (n_rows == 0 || q == 0)
         return 0;
     if (q > 0xffffffffull)
         return YUME_PDQ_CUDA_E_INVALID;
-    Sink sink{out, cap, count, min_key, row_offset, (uint64_t)q, mode};
+    Sink sink{out, cap, count, min_key, row_offset, (uint64_t)q, mode, needle_base};
     const uint4 *rows4 = reinterpret_cast<const uint4 *>(rows);
     const uint4 *needles4 = reinterpret_cast<const uint4 *>(needles);
     if (algo == YUME_PDQ_CUDA_ALGO_AUTO) {
@@ -431,10 +440,10 @@ int launch_match(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const 
         algo = YUME_PDQ_CUDA_ALGO_TILED;
     if (algo == YUME_PDQ_CUDA_ALGO_TENSOR && threshold <= 127)
         return launch_match_tensor4(rows, n_rows, row_offset, needles, q, threshold, out, cap, count, min_key,
-                                    mode, sm_count, s);
+                                    mode, sm_count, s, needle_base);
     if (algo == YUME_PDQ_CUDA_ALGO_TENSOR || algo == YUME_PDQ_CUDA_ALGO_TENSOR_I8)
         return launch_match_tensor(rows, n_rows, row_offset, needles, q, threshold, out, cap, count, min_key,
-                                   mode, sm_count, s);
+                                   mode, sm_count, s, needle_base);
 
     if (algo == YUME_PDQ_CUDA_ALGO_EXACT) {
         dim3 grid((unsigned)((n_rows + EX_THREADS * EX_ROWS - 1) / (EX_THREADS * EX_ROWS)),
@@ -445,10 +454,32 @@ int launch_match(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const 
         return 0;
     }
     if (algo == YUME_PDQ_CUDA_ALGO_TILED) {
-        dim3 grid((unsigned)((n_rows + TL_THREADS * TL_ROWS - 1) / (TL_THREADS * TL_ROWS)),
-                  (unsigned)((q + TL_NCHUNK - 1) / TL_NCHUNK));
-        match_tiled_kernel<<<grid, TL_THREADS, 0, s>>>(rows4, n_rows, needles4, (uint32_t)q,
-                                                       threshold, sink);
+        // 4 rows per thread and >= 6 resident CTAs per SM overlap one CTA's HBM loads with the others'
+        // popcounts (10M rows x 8 needles: 55 us vs 74 us with 8 rows / 116 registers)
+        static const int variant = [] {
+            const char *e = getenv("YPDQ_TILED_VARIANT");   // developer knob for tools/quick_bench.py
+            return e ? atoi(e) : -1;
+        }();
+        const int v = variant >= 0 ? variant : TL_DEFAULT_VARIANT;
+#define LAUNCH_TILED(R, B)                                                                         \
+    do {                                                                                          \
+        dim3 grid((unsigned)((n_rows + TL_THREADS * R - 1) / (TL_THREADS * R)),                   \
+                  (unsigned)((q + TL_NCHUNK - 1) / TL_NCHUNK));                                   \
+        const size_t smem = std::min<size_t>(q, TL_NCHUNK) * sizeof(uint4) + TL_QCAP * sizeof(uint32_t); \
+        match_tiled_kernel<R, B><<<grid, TL_THREADS, smem, s>>>(rows4, n_rows, needles4, (uint32_t)q, \
+                                                             threshold, sink);                    \
+    } while (0)
+        switch (v) {
+        case 1: LAUNCH_TILED(8, 4); break;
+        case 2: LAUNCH_TILED(4, 4); break;
+        case 3: LAUNCH_TILED(4, 6); break;
+        case 4: LAUNCH_TILED(4, 8); break;
+        case 5: LAUNCH_TILED(2, 8); break;
+        case 6: LAUNCH_TILED(16, 2); break;
+        case 7: LAUNCH_TILED(8, 3); break;
+        default: LAUNCH_TILED(8, 1); break;
+        }
+#undef LAUNCH_TILED
         YPDQ_LAUNCH_CHECK();
         return 0;
     }

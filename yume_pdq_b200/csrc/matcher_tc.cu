@@ -128,6 +128,7 @@ struct TcSink {
     uint64_t row_offset;
     uint64_t q;
     int mode;
+    uint32_t needle_base;   // added to reported needle indices (LIST mode): pipelined callers match in chunks
 };
 
 __device__ __forceinline__ void tc_emit(const TcSink &k, uint64_t local_row, uint32_t needle, uint32_t dist)
@@ -138,7 +139,7 @@ __device__ __forceinline__ void tc_emit(const TcSink &k, uint64_t local_row, uin
     } else if (pos < k.cap) {
         YumePDQ_Match m;
         m.row = local_row + k.row_offset;
-        m.needle = needle;
+        m.needle = needle + k.needle_base;
         m.dist = dist;
         k.out[pos] = m;
     }
@@ -314,7 +315,7 @@ match_tensor_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint8
 
 int launch_match_tensor(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles, size_t q,
                         uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
-                        unsigned long long *min_key, int mode, int sm_count, cudaStream_t s)
+                        unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base)
 {
     if (n_rows == 0 || q == 0)
         return 0;
@@ -334,7 +335,7 @@ int launch_match_tensor(const uint8_t *rows, size_t n_rows, uint64_t row_offset,
         YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
         attr_set = true;
     }
-    TcSink sink{out, cap, count, min_key, row_offset, (uint64_t)q, mode};
+    TcSink sink{out, cap, count, min_key, row_offset, (uint64_t)q, mode, needle_base};
     const uint64_t n_ntiles = (n_rows + TC_N - 1) / TC_N;
     const unsigned grid = (unsigned)std::min<uint64_t>(n_ntiles, (uint64_t)sm_count);
     const int32_t dot_min = 256 - 2 * (int32_t)std::min<uint32_t>(threshold, 256u);

@@ -141,6 +141,7 @@ struct Tc4Sink {
     uint64_t row_offset;
     uint64_t q;
     int mode;
+    uint32_t needle_base;   // added to reported needle indices (LIST mode): pipelined callers match in chunks
 };
 
 __device__ __forceinline__ void tc4_emit(const Tc4Sink &k, uint64_t local_row, uint32_t needle, uint32_t dist)
@@ -151,7 +152,7 @@ __device__ __forceinline__ void tc4_emit(const Tc4Sink &k, uint64_t local_row, u
     } else if (pos < k.cap) {
         YumePDQ_Match m;
         m.row = local_row + k.row_offset;
-        m.needle = needle;
+        m.needle = needle + k.needle_base;
         m.dist = dist;
         k.out[pos] = m;
     }
@@ -205,10 +206,11 @@ __device__ __forceinline__ void load_batch(int32_t (&v)[T4_EB], uint32_t taddr)
 __device__ __forceinline__ void process_batch(const int32_t (&v)[T4_EB], int32_t min_bits, uint64_t row0,
                                               uint64_t n_rows, uint32_t needle, uint32_t q, const Tc4Sink &sink)
 {
-    int32_t mx = v[0];
+    int32_t m4[4] = {v[0], v[1], v[2], v[3]};   // four independent max chains (ILP), VIMNMX3
 #pragma unroll
-    for (int j = 1; j < T4_EB; j++)
-        mx = max(mx, v[j]);
+    for (int j = 4; j < T4_EB; j++)
+        m4[j & 3] = max(m4[j & 3], v[j]);
+    const int32_t mx = max(max(m4[0], m4[1]), max(m4[2], m4[3]));
     if (mx >= min_bits && needle < q) {  // rare: some row of this batch matches this needle
 #pragma unroll
         for (int j = 0; j < T4_EB; j++) {
@@ -371,37 +373,23 @@ match_tensor4_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint
         int32_t va[T4_EB], vb[T4_EB];
         uint64_t st = blockIdx.x;
         uint32_t m = 0, t = 0;
-        if (total > 0) {
-            bar_wait(&d_full[0], 0);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            load_batch(va, lane_base);
-        }
         for (uint64_t id = 0; id < total; id++) {
             const uint32_t acc = (uint32_t)id & 1u;
             const uint32_t needle = m * T4_M + quad * 32 + lane;
             const uint64_t row0 = st * T4_ROWS + t * T4_N + half * T4_EW;
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            bar_wait(&d_full[acc], (uint32_t)(id >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // all 120 columns of this warp in flight at once: the accumulator stage is held for one
+            // TMEM-load latency only, then handed back to the MMA issuer before any arithmetic
+            load_batch(va, lane_base + acc * T4_N);
             load_batch(vb, lane_base + acc * T4_N + T4_EB);
-            process_batch(va, min_bits, row0, n_rows, needle, q, sink);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0)
-                bar_arrive(&d_empty[acc]);     // every TMEM read of this accumulator has completed
-            const bool more = id + 1 < total;
-            const uint32_t nacc = acc ^ 1u, npar = (uint32_t)((id + 1) >> 1) & 1u;
-            bool issued = false;
-            if (more && bar_try(&d_full[nacc], npar)) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                load_batch(va, lane_base + nacc * T4_N);
-                issued = true;
-            }
+                bar_arrive(&d_empty[acc]);
+            process_batch(va, min_bits, row0, n_rows, needle, q, sink);
             process_batch(vb, min_bits, row0 + T4_EB, n_rows, needle, q, sink);
-            if (more && !issued) {
-                bar_wait(&d_full[nacc], npar);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                load_batch(va, lane_base + nacc * T4_N);
-            }
             // advance (t fastest, then m, then super-tile) -- the MMA issue order
             if (++t == T4_NB) {
                 t = 0;
@@ -423,7 +411,7 @@ match_tensor4_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint
 
 int launch_match_tensor4(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles, size_t q,
                          uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
-                         unsigned long long *min_key, int mode, int sm_count, cudaStream_t s)
+                         unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base)
 {
     if (n_rows == 0 || q == 0)
         return 0;
@@ -445,7 +433,7 @@ int launch_match_tensor4(const uint8_t *rows, size_t n_rows, uint64_t row_offset
         YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM));
         attr_set = true;
     }
-    Tc4Sink sink{out, cap, count, min_key, row_offset, (uint64_t)q, mode};
+    Tc4Sink sink{out, cap, count, min_key, row_offset, (uint64_t)q, mode, needle_base};
     const uint64_t n_stiles = (n_rows + T4_ROWS - 1) / T4_ROWS;
     const unsigned grid = (unsigned)std::min<uint64_t>(n_stiles, (uint64_t)sm_count);
     const float dot_min = (float)(256 - 2 * (int32_t)threshold);
