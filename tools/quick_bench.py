@@ -63,6 +63,50 @@ def main():
                   f"best {best:8.1f} us  {n * 32 / med / 1e3:7.1f} GB/s  {n * q / med / 1e6:8.3f} Tpairs/s   "
                   f"[back-to-back, no flush: median {med2:8.1f} us best {best2:8.1f}]")
         db.close()
+    if "tc4v" in what:   # packed-FP4 tensor matcher variants (YPDQ_TC4_VARIANT, one process per variant)
+        n = (10_000_000 // 2048 + 1) * 2048
+        db = yp.CudaVectorDatabase(synthetic_rows=n)
+        m = yp.CudaMatcher(db, 31)
+        out = torch.zeros((1 << 20, 16), dtype=torch.uint8, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for q in (1024, 4096, 32768):
+            needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
+            med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 20, cnt, algo=yp.ALGO_TENSOR), iters=5, warm=1)
+            print(f"tc4 variant {os.environ.get('YPDQ_TC4_VARIANT', '-')}: match 10M x {q:6d}: median {med / 1e3:9.2f} ms  "
+                  f"{n * q / med / 1e6:8.3f} Tpairs/s  hits={int(cnt.item())}")
+            cnt.zero_()
+        db.close()
+    if "tc4clk" in what:   # SM clock / power while the tensor matcher runs back to back for ~1.5 s
+        import subprocess, tempfile
+        n = (10_000_000 // 2048 + 1) * 2048
+        db = yp.CudaVectorDatabase(synthetic_rows=n)
+        m = yp.CudaMatcher(db, 31)
+        out = torch.zeros((1 << 20, 16), dtype=torch.uint8, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        needles = torch.from_numpy(rng.integers(0, 256, size=(32768, 32), dtype=np.uint8)).cuda()
+        for name, algo in (("mxf4", yp.ALGO_TENSOR), ("i8", yp.ALGO_TENSOR_I8), ("tiled", yp.ALGO_TILED)):
+            f = tempfile.NamedTemporaryFile("w+", suffix=".csv")
+            p = subprocess.Popen(["nvidia-smi", "-i", "0", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap,"
+                                  "clocks_event_reasons.hw_slowdown,clocks_event_reasons.sw_thermal_slowdown",
+                                  "--format=csv,noheader,nounits", "-lms", "50"], stdout=f)
+            time.sleep(0.3)
+            t0 = time.time()
+            reps = 0
+            while time.time() - t0 < 1.5:
+                m.find_device(needles, 32768, out, 1 << 20, cnt, algo=algo)
+                torch.cuda.synchronize()
+                reps += 1
+            dt = time.time() - t0
+            p.terminate(); p.wait()
+            f.seek(0)
+            rowsv = [l.split(",") for l in f.read().splitlines() if l.strip()]
+            clk = sorted(float(r[0]) for r in rowsv[4:])
+            pw = sorted(float(r[1]) for r in rowsv[4:])
+            cap = sum(1 for r in rowsv[4:] if "Active" in r[2] and "Not" not in r[2])
+            print(f"{name}: {reps} launches in {dt:.2f} s = {dt / reps * 1e3:.2f} ms each, {n * 32768 * reps / dt / 1e12:.2f} Tpairs/s; "
+                  f"SM clock median {clk[len(clk) // 2]:.0f} MHz (min {clk[0]:.0f}), power median {pw[len(pw) // 2]:.0f} W "
+                  f"(max {pw[-1]:.0f}), sw_power_cap active in {cap}/{len(rowsv) - 4} samples")
+        db.close()
     if "tiled" in what:
         n = (10_000_000 // 2048 + 1) * 2048
         db = yp.CudaVectorDatabase(synthetic_rows=n)

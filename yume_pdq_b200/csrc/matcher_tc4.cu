@@ -9,18 +9,21 @@
 // of 17.4e12 (row, needle) pairs/s instead of 8.9e12.
 //
 // Persistent kernel, one CTA per SM, 12 warps, warp-specialised:
-//   warp 0       A producer: streams pre-expanded needle tiles (128 needles x 128 B = 16 KB, canonical
+//   warp 10      A producer: streams pre-expanded needle tiles (128 needles x 128 B = 16 KB, canonical
 //                K-major SWIZZLE_NONE layout) from L2 into a 4-stage shared-memory ring with TMA bulk copies
-//   warp 1       MMA issuer: per (needle tile, row tile) 4 x tcgen05.mma (M 128, N 240, K 64) into one of two
+//   warp 11      MMA issuer: per (needle tile, row tile) 4 x tcgen05.mma (M 128, N 240, K 64) into one of two
 //                240-column TMEM accumulators; tcgen05.commit -> mbarriers
-//   warps 2-3    B expanders: turn the CTA's next 480 database rows (15 KB of bits) into two 30 KB e2m1
+//   warps 8-9    B expanders: turn the CTA's next 480 database rows (15 KB of bits) into two 30 KB e2m1
 //                row tiles (double buffered); each needle tile is streamed ONCE per 480 rows
-//   warps 4-11   epilogue: tcgen05.ld (lane = needle, column = row), 3-input max tree over the raw f32
-//                bits, rare hit path with exact distance = (256 - dot) / 2
+//   warps 0-7    epilogue: tcgen05.ld (lane = needle, column = row; 120 columns per warp), 3-input max tree
+//                over the raw f32 bits, rare hit path with exact distance = (256 - dot) / 2
 // Shared memory: 2 x 60 KB (B) + 4 x 16 KB (A) = 184 KB.  TMEM: 2 x 240 accumulator columns + 32 columns
 // of scale factors (every byte 0x7F = 2^0, so the scale-factor layout is irrelevant).
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -36,9 +39,16 @@ constexpr int T4_A_BYTES = T4_M * T4_ROW_BYTES;      // 16 KB
 constexpr int T4_B_BYTES = T4_N * T4_ROW_BYTES;      // 30 KB
 constexpr int T4_SB_BYTES = T4_NB * T4_B_BYTES;      // 60 KB per super-tile buffer
 constexpr int T4_A_STAGES = 4;
-constexpr int T4_EPI_WARPS = 8;
-constexpr int T4_EXP_THREADS = 64;          // B expander threads (warps 2-3)
-constexpr int T4_THREADS = 64 + T4_EXP_THREADS + 32 * T4_EPI_WARPS;  // 384 -> up to 168 registers per thread
+#ifndef T4_EPI_WARPS_CFG
+#define T4_EPI_WARPS_CFG 8
+#endif
+constexpr int T4_EPI_WARPS = T4_EPI_WARPS_CFG;   // 8: 2 per TMEM lane quadrant x 120 accumulator columns; 16: 4 x 60
+constexpr int T4_EXP_THREADS = 64;          // B expander threads (the two warps after the epilogue warps)
+// The warp scheduler favours the highest warp id among eligible warps, so the latency-critical single-thread
+// roles get the highest ids: with the MMA issuer as warp 1 the epilogue warps sharing its scheduler delayed
+// every tcgen05.mma issue by their own arithmetic (12.3e12 pairs/s).
+constexpr int T4_WARP_PRODUCER = T4_EPI_WARPS + 2, T4_WARP_MMA = T4_EPI_WARPS + 3;
+constexpr int T4_THREADS = 64 + T4_EXP_THREADS + 32 * T4_EPI_WARPS;  // 384 threads (up to 168 registers) or 640 (102)
 constexpr uint32_t T4_LBO = 128;           // bytes between K-adjacent core matrices (16-byte chunks)
 constexpr uint32_t T4_SBO = 1024;          // bytes between 8-row groups
 constexpr uint32_t T4_SF_COL = 480;        // TMEM columns 480..511: scale factors
@@ -73,6 +83,24 @@ __device__ __forceinline__ void bar_wait(uint64_t *b, uint32_t parity)
 {
     while (!bar_try(b, parity)) {
     }
+}
+// hot-loop forms on precomputed shared-window addresses (the generic->shared conversion costs an S2R + LEA
+// per use otherwise); the wait is one PTX block, try_wait parks the warp in hardware between polls
+__device__ __forceinline__ void bar_wait_addr(uint32_t addr, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "T4_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra T4_DONE;\n\t"
+        "bra T4_WAIT;\n"
+        "T4_DONE:\n\t}" ::"r"(addr),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bar_arrive_addr(uint32_t addr)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *b)
 {
@@ -170,6 +198,10 @@ __device__ __forceinline__ void tc4_emit(const Tc4Sink &k, uint64_t local_row, u
           "=r"(v[o + 24]), "=r"(v[o + 25]), "=r"(v[o + 26]), "=r"(v[o + 27]), "=r"(v[o + 28]), "=r"(v[o + 29]), \
           "=r"(v[o + 30]), "=r"(v[o + 31])                                                                     \
         : "r"(taddr))
+#define T4_LD_X64(v, o, taddr) \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];" \
+                 : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7]), "=r"(v[o + 8]), "=r"(v[o + 9]), "=r"(v[o + 10]), "=r"(v[o + 11]), "=r"(v[o + 12]), "=r"(v[o + 13]), "=r"(v[o + 14]), "=r"(v[o + 15]), "=r"(v[o + 16]), "=r"(v[o + 17]), "=r"(v[o + 18]), "=r"(v[o + 19]), "=r"(v[o + 20]), "=r"(v[o + 21]), "=r"(v[o + 22]), "=r"(v[o + 23]), "=r"(v[o + 24]), "=r"(v[o + 25]), "=r"(v[o + 26]), "=r"(v[o + 27]), "=r"(v[o + 28]), "=r"(v[o + 29]), "=r"(v[o + 30]), "=r"(v[o + 31]), "=r"(v[o + 32]), "=r"(v[o + 33]), "=r"(v[o + 34]), "=r"(v[o + 35]), "=r"(v[o + 36]), "=r"(v[o + 37]), "=r"(v[o + 38]), "=r"(v[o + 39]), "=r"(v[o + 40]), "=r"(v[o + 41]), "=r"(v[o + 42]), "=r"(v[o + 43]), "=r"(v[o + 44]), "=r"(v[o + 45]), "=r"(v[o + 46]), "=r"(v[o + 47]), "=r"(v[o + 48]), "=r"(v[o + 49]), "=r"(v[o + 50]), "=r"(v[o + 51]), "=r"(v[o + 52]), "=r"(v[o + 53]), "=r"(v[o + 54]), "=r"(v[o + 55]), "=r"(v[o + 56]), "=r"(v[o + 57]), "=r"(v[o + 58]), "=r"(v[o + 59]), "=r"(v[o + 60]), "=r"(v[o + 61]), "=r"(v[o + 62]), "=r"(v[o + 63]) \
+                 : "r"(taddr))
 #define T4_LD_X16(v, o, taddr)                                                                                 \
     asm volatile(                                                                                              \
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                              \
@@ -188,38 +220,45 @@ __device__ __forceinline__ void tc4_emit(const Tc4Sink &k, uint64_t local_row, u
                  : "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3])                              \
                  : "r"(taddr))
 
-constexpr int T4_EW = T4_N / 2;      // 120 columns per epilogue warp
-constexpr int T4_EB = T4_EW / 2;     // 60 columns per register batch
+constexpr int T4_EB = T4_N / (T4_EPI_WARPS / 4);   // accumulator columns per epilogue warp: 120 or 60
+static_assert(T4_EB == 60 || T4_EB == 120, "load_batch is written for 60 or 120 columns");
 
-// 60 consecutive accumulator columns of this warp's 32 lanes -> v[0..59] (asynchronous; needs wait::ld)
+// T4_EB consecutive accumulator columns of this warp's 32 lanes -> v (asynchronous; needs wait::ld)
 __device__ __forceinline__ void load_batch(int32_t (&v)[T4_EB], uint32_t taddr)
 {
-    T4_LD_X32(v, 0, taddr);
-    T4_LD_X16(v, 32, taddr + 32);
-    T4_LD_X8(v, 48, taddr + 48);
-    T4_LD_X4(v, 56, taddr + 56);
+    if constexpr (T4_EB == 120) {
+        T4_LD_X64(v, 0, taddr);
+        T4_LD_X32(v, 64, taddr + 64);
+        T4_LD_X16(v, 96, taddr + 96);
+        T4_LD_X8(v, 112, taddr + 112);
+    } else {
+        T4_LD_X32(v, 0, taddr);
+        T4_LD_X16(v, 32, taddr + 32);
+        T4_LD_X8(v, 48, taddr + 48);
+        T4_LD_X4(v, 56, taddr + 56);
+    }
 }
 
-// v holds raw f32 bits of exact integer dot products.  For dot_min > 0 a signed-integer compare of the raw
-// bits against the bits of dot_min is the f32 compare (all non-negative floats order like their bits and
-// every negative float has the sign bit set).
-__device__ __forceinline__ void process_batch(const int32_t (&v)[T4_EB], int32_t min_bits, uint64_t row0,
-                                              uint64_t n_rows, uint32_t needle, uint32_t q, const Tc4Sink &sink)
+__device__ __forceinline__ bool batch_any(const int32_t (&v)[T4_EB], int32_t min_bits)
 {
-    int32_t m4[4] = {v[0], v[1], v[2], v[3]};   // four independent max chains (ILP), VIMNMX3
+    int32_t m4[4] = {v[0], v[1], v[2], v[3]};
 #pragma unroll
     for (int j = 4; j < T4_EB; j++)
         m4[j & 3] = max(m4[j & 3], v[j]);
-    const int32_t mx = max(max(m4[0], m4[1]), max(m4[2], m4[3]));
-    if (mx >= min_bits && needle < q) {  // rare: some row of this batch matches this needle
+    return max(max(m4[0], m4[1]), max(m4[2], m4[3])) >= min_bits;
+}
+
+// rare path: some row of this batch matches this needle
+__device__ __forceinline__ void report_hits(const int32_t (&v)[T4_EB], int32_t min_bits, uint64_t row0, uint64_t n_rows,
+                                         uint32_t needle, const Tc4Sink &sink)
+{
 #pragma unroll
-        for (int j = 0; j < T4_EB; j++) {
-            if (v[j] >= min_bits) {
-                const uint64_t row = row0 + j;
-                if (row < n_rows) {
-                    const int32_t dot = (int32_t)__int_as_float(v[j]);
-                    tc4_emit(sink, row, needle, (uint32_t)(256 - dot) >> 1);
-                }
+    for (int j = 0; j < T4_EB; j++) {
+        if (v[j] >= min_bits) {
+            const uint64_t row = row0 + j;
+            if (row < n_rows) {
+                const int32_t dot = (int32_t)__int_as_float(v[j]);
+                tc4_emit(sink, row, needle, (uint32_t)(256 - dot) >> 1);
             }
         }
     }
@@ -251,7 +290,7 @@ match_tensor4_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == T4_WARP_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -259,7 +298,7 @@ match_tensor4_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
-    if (warp >= 4 && warp < 8) {
+    if (warp < 4) {
         // scale factors: ue8m0 0x7F = 1.0 in every byte of columns 480..511 of all 128 lanes
         const uint32_t base = tmem + (((uint32_t)(warp & 3) * 32u) << 16) + T4_SF_COL;
         const uint32_t one = 0x7F7F7F7Fu;
@@ -274,7 +313,7 @@ match_tensor4_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint
 
     const uint64_t n_stiles = (n_rows + T4_ROWS - 1) / T4_ROWS;
 
-    if (warp == 0) {
+    if (warp == T4_WARP_PRODUCER) {
         // ===== A producer =====
         if (lane == 0) {
             uint32_t it = 0;
@@ -286,7 +325,7 @@ match_tensor4_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint
                     bulk_g2s(sA + (size_t)s * T4_A_BYTES, needles_exp + (size_t)m * T4_A_BYTES, T4_A_BYTES, &a_full[s]);
                 }
         }
-    } else if (warp == 1) {
+    } else if (warp == T4_WARP_MMA) {
         // ===== MMA issuer =====
         if (lane == 0) {
             uint32_t ia = 0, id = 0, i = 0;
@@ -325,9 +364,9 @@ match_tensor4_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint
                 umma_commit(&b_empty[b]);             // B buffer may be overwritten
             }
         }
-    } else if (warp < 4) {
+    } else if (warp >= T4_EPI_WARPS) {
         // ===== B expanders: 64 threads, thread t expands rows t, t+64, ... of the super-tile, 4 rows at a time =====
-        const uint32_t t = threadIdx.x - 64;
+        const uint32_t t = threadIdx.x - 32 * T4_EPI_WARPS;
         uint32_t i = 0;
         for (uint64_t st = blockIdx.x; st < n_stiles; st += gridDim.x, i++) {
             const uint32_t b = i & 1u;
@@ -365,45 +404,46 @@ match_tensor4_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint
             bar_arrive(&b_full[b]);
         }
     } else {
-        // ===== epilogue: TMEM lane quadrant = warp % 4, column half = (warp - 4) / 4 =====
-        const uint32_t quad = warp & 3u, half = (uint32_t)(warp - 4) >> 2;
-        const uint32_t lane_base = tmem + ((quad * 32u) << 16) + half * T4_EW;
-        const uint64_t my_tiles = blockIdx.x < n_stiles ? (n_stiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-        const uint64_t total = my_tiles * n_mtiles * T4_NB;   // accumulator tiles this CTA produces
-        int32_t va[T4_EB], vb[T4_EB];
-        uint64_t st = blockIdx.x;
-        uint32_t m = 0, t = 0;
-        for (uint64_t id = 0; id < total; id++) {
-            const uint32_t acc = (uint32_t)id & 1u;
-            const uint32_t needle = m * T4_M + quad * 32 + lane;
-            const uint64_t row0 = st * T4_ROWS + t * T4_N + half * T4_EW;
-            bar_wait(&d_full[acc], (uint32_t)(id >> 1) & 1u);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // all 120 columns of this warp in flight at once: the accumulator stage is held for one
-            // TMEM-load latency only, then handed back to the MMA issuer before any arithmetic
-            load_batch(va, lane_base + acc * T4_N);
-            load_batch(vb, lane_base + acc * T4_N + T4_EB);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0)
-                bar_arrive(&d_empty[acc]);
-            process_batch(va, min_bits, row0, n_rows, needle, q, sink);
-            process_batch(vb, min_bits, row0 + T4_EB, n_rows, needle, q, sink);
-            // advance (t fastest, then m, then super-tile) -- the MMA issue order
-            if (++t == T4_NB) {
-                t = 0;
-                if (++m == n_mtiles) {
-                    m = 0;
-                    st += gridDim.x;
+        // ===== epilogue: TMEM lane quadrant = warp % 4, column part = warp / 4 =====
+        // 16 warps, 4 per scheduler: while one waits for its TMEM load the others run their max trees.
+        const uint32_t quad = warp & 3u, part = (uint32_t)warp >> 2;
+        const uint32_t lane_base = tmem + ((quad * 32u) << 16) + part * T4_EB;
+        const uint32_t my_stiles =
+            blockIdx.x < n_stiles ? (uint32_t)((n_stiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+        const uint32_t per_stile = n_mtiles * T4_NB;          // accumulator tiles per super-tile (even)
+        uint32_t dfull = s32(&d_full[0]), dempty = s32(&d_empty[0]), tbase = lane_base;
+        int32_t mb = min_bits;
+        asm volatile("" : "+r"(dfull), "+r"(dempty), "+r"(tbase), "+r"(mb));   // keep them in registers (no rematerialisation)
+        int32_t v[T4_EB];
+        uint32_t parity = 0;
+        for (uint32_t si = 0; si < my_stiles; si++) {
+            for (uint32_t mt = 0; mt < per_stile; mt += 2) {       // mt = m * T4_NB + t; accumulator stage = mt & 1
+#pragma unroll
+                for (uint32_t acc = 0; acc < 2; acc++) {
+                    bar_wait_addr(dfull + 8 * acc, parity);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    load_batch(v, tbase + acc * T4_N);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    // the accumulator stage goes back to the MMA issuer before any arithmetic
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    if (lane == 0)
+                        bar_arrive_addr(dempty + 8 * acc);
+                    if (batch_any(v, mb)) {
+                        const uint32_t needle = (mt / T4_NB) * T4_M + quad * 32 + lane;
+                        if (needle < q) {
+                            const uint64_t st = blockIdx.x + (uint64_t)si * gridDim.x;
+                            report_hits(v, min_bits, st * T4_ROWS + acc * T4_N + part * T4_EB, n_rows, needle, sink);
+                        }
+                    }
                 }
+                parity ^= 1u;
             }
         }
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1)
+    if (warp == T4_WARP_MMA)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
@@ -428,17 +468,17 @@ int launch_match_tensor4(const uint8_t *rows, size_t n_rows, uint64_t row_offset
     expand_needles4_kernel<<<(threads + 255) / 256, 256, 0, s>>>(reinterpret_cast<const uint4 *>(needles), (uint32_t)q, exp,
                                                                  n_mtiles);
     YPDQ_LAUNCH_CHECK();
-    static bool attr_set = false;
-    if (!attr_set) {
-        YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM));
-        attr_set = true;
-    }
     Tc4Sink sink{out, cap, count, min_key, row_offset, (uint64_t)q, mode, needle_base};
     const uint64_t n_stiles = (n_rows + T4_ROWS - 1) / T4_ROWS;
     const unsigned grid = (unsigned)std::min<uint64_t>(n_stiles, (uint64_t)sm_count);
     const float dot_min = (float)(256 - 2 * (int32_t)threshold);
     int32_t min_bits;
     memcpy(&min_bits, &dot_min, 4);
+    static bool attr_set = false;
+    if (!attr_set) {
+        YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T4_SMEM));
+        attr_set = true;
+    }
     match_tensor4_kernel<<<grid, T4_THREADS, T4_SMEM, s>>>(reinterpret_cast<const uint4 *>(rows), n_rows, exp, n_mtiles,
                                                            (uint32_t)q, min_bits, sink);
     YPDQ_LAUNCH_CHECK();
