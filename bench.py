@@ -252,9 +252,11 @@ def main():
     from yume_pdq_b200 import sharded
     row0, row1 = sharded.shard_range(DB_ROWS, rank, n_gpus)
     shard_rows = row1 - row0
-    db = yp.CudaVectorDatabase(device=local_rank, global_row_offset=row0, synthetic_rows=shard_rows,
-                               seed=SEED)
-    matcher = yp.CudaMatcher(db, THRESHOLD)
+    sm = sharded.ShardedMatcher(
+        DB_ROWS, THRESHOLD,
+        lambda b, e, d: yp.CudaVectorDatabase(device=d, global_row_offset=b, synthetic_rows=e - b, seed=SEED),
+        device=local_rank)
+    db, matcher = sm.db, sm.matcher
     outs = {"hashes": torch.empty((B, 8, 32), dtype=torch.uint8, device=dev),
             "quality": torch.empty((B, 8), dtype=torch.float32, device=dev),
             "thresholds": torch.empty((B, 8), dtype=torch.float32, device=dev)}
@@ -412,17 +414,17 @@ def main():
         host_frames = torch.empty((B, 512, 512), dtype=torch.float32, pin_memory=True)
         host_frames.copy_(frames)
         host_hashes = np.zeros((B, 8, 32), dtype=np.uint8)
-        hk = yp.CudaKernel(local_rank)
+        host_hashes_t = torch.from_numpy(host_hashes)
 
         def e2e_step():
             if n_gpus == 1:
                 # one pipelined C-ABI call: H2D of chunk i+1 overlaps hash + match of chunk i
                 return matcher.screen(host_frames.numpy(), hashes=host_hashes)
-            hk.hash_batch(host_frames.numpy(), want_quality=False, want_thresholds=False,
-                          out={"hashes": host_hashes})
-            nt = torch.from_numpy(host_hashes.reshape(-1, 32)).to(dev)
-            dist.all_gather_into_tensor(needles_all, nt)
-            return matcher.find_all(needles_all)
+            # the same pipeline across ranks: chunked H2D || hash -> NCCL all-gather -> match vs the shard,
+            # then the gather + merge of the match lists (yume_pdq_b200/sharded.py)
+            m = sm.screen(host_frames, hashes_out=outs["hashes"])
+            host_hashes_t.copy_(outs["hashes"])
+            return m
 
         e2e_step()
         barrier()
@@ -437,11 +439,13 @@ def main():
         dt = float(tt.item())
         e2e = {"value": n_gpus * B * e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(B * 512 * 512 * 4 + B * 8 * 32),
-               "d2h_bytes_per_step": int(B * 8 * 32 + 16 + len(m) * 16),
+               "d2h_bytes_per_step": int(B * 8 * 32 + 16 + len(m) * 16) if n_gpus == 1 else
+               int(B * 8 * 32 + 4 + (1 << 16) * 16 * n_gpus),
                "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
                "path": ("yume_pdq_cuda_screen_batch(pinned host frames -> host hashes + sorted host match list)"
                         if n_gpus == 1 else
-                        "yume_pdq_cuda_hash_batch(host frames) + NCCL all-gather + yume_pdq_cuda_matcher_find")}
+                        "ShardedMatcher.screen(pinned host frames): chunked H2D || yume_pdq_cuda_hash_batch -> NCCL "
+                        "all-gather -> yume_pdq_cuda_matcher_find_device_base, then gather + merge of match lists")}
         del host_frames
 
     cpu_bl = None

@@ -205,6 +205,13 @@ int yume_pdq_cuda_matcher_find_device(YumePDQ_CudaDb *db, const uint8_t *needles
                                       uint32_t threshold, YumePDQ_Match *out_dev, uint32_t cap,
                                       uint32_t *count_dev, int algo, void *stream);
 
+/* Same, with `needle_base` added to every reported needle index: callers that match a long needle
+ * stream in chunks (yume_pdq_b200/sharded.py pipelines chunked all-gathers against the local shard)
+ * append to one list without a renumbering pass on the device. */
+int yume_pdq_cuda_matcher_find_device_base(YumePDQ_CudaDb *db, const uint8_t *needles_dev, size_t q,
+                                           uint32_t threshold, YumePDQ_Match *out_dev, uint32_t cap,
+                                           uint32_t *count_dev, int algo, uint32_t needle_base, void *stream);
+
 /* Hash + match in one pipelined call: the flow of examples/end_to_end.rs:224-256 (hash_get_threshold ->
  * visit_dihedrals -> matcher.find for every frame) for a whole batch.  frames n x 512 x 512 f32, host or
  * device; host frames are copied in 128-frame chunks and chunk i's hash + match kernels overlap the copy

@@ -1,0 +1,81 @@
+"""Two-GPU parity of the sharded pipeline (NCCL, one process per GPU): ShardedMatcher.screen /
+find_all / scan against the CPU oracle on the unsharded problem.  Skipped on a single-GPU box (the
+host-side logic is covered on CPU by tests/test_sharded_gloo.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from helpers import flip_bits, match_tuples
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_local, n_rows, result_dir):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (here, os.path.dirname(here)):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+
+    import yume_pdq_b200 as yp
+    from oracle import pyoracle
+    from yume_pdq_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    orc = pyoracle.get()
+    # every rank derives the same global problem with the oracle
+    frames_all = orc.synth_frames(world * n_local, first_frame=500, kind=1)
+    wh, _, _, _ = orc.hash_all_dihedrals(frames_all)
+    needles_all = wh.reshape(-1, 32)
+    rng = np.random.default_rng(17)
+    rows = orc.synth_db(n_rows, first_row=3)
+    for r in rng.choice(n_rows, size=120, replace=False):
+        rows[r] = flip_bits(needles_all[int(rng.integers(0, needles_all.shape[0]))], int(rng.integers(0, 35)), rng)
+    want = match_tuples(orc.matcher_find(rows, needles_all, 31))
+    assert len(want) > 60
+
+    def factory(begin, end, device):
+        return yp.CudaVectorDatabase(rows[begin:end], device=device, global_row_offset=begin)
+
+    sm = sharded.ShardedMatcher(n_rows, 31, factory, device=rank)
+    mine = frames_all[rank * n_local:(rank + 1) * n_local]
+    # host frames (pinned) through the chunked pipeline, partial last chunk
+    pinned = torch.from_numpy(mine.copy()).pin_memory()
+    hd = torch.zeros((n_local, 8, 32), dtype=torch.uint8, device=f"cuda:{rank}")
+    got = sm.screen(pinned, hashes_out=hd, chunk=64)
+    assert np.array_equal(hd.cpu().numpy(), wh[rank * n_local:(rank + 1) * n_local])
+    assert match_tuples(got) == want
+    # device frames, capacity growth
+    got2 = sm.screen(torch.from_numpy(mine).cuda(), cap=8, chunk=64)
+    assert match_tuples(got2) == want
+    # the two-call path: hash, all-gather, find
+    assert match_tuples(sm.find_all(hd.reshape(-1, 32))) == want
+    assert sm.scan(hd.reshape(-1, 32)) is True
+    sm.close()
+    np.save(os.path.join(result_dir, f"ok{rank}.npy"), np.array([len(got)]))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_screen(tmp_path, oracle):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), 150, 60_001, str(tmp_path)), nprocs=world, join=True)
+    counts = [int(np.load(tmp_path / f"ok{r}.npy")[0]) for r in range(world)]
+    assert counts[0] == counts[1] > 60

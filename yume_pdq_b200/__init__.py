@@ -94,6 +94,8 @@ SIGNATURES = {
                                                  C.POINTER(C.c_uint64), _vp]),
     "yume_pdq_cuda_matcher_find_device": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _vp, C.c_uint32,
                                                     _vp, C.c_int, _vp]),
+    "yume_pdq_cuda_matcher_find_device_base": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _vp, C.c_uint32,
+                                                         _vp, C.c_int, C.c_uint32, _vp]),
     "yume_pdq_cuda_screen_batch": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _vp, _vp, _vp, C.c_size_t,
                                              C.POINTER(C.c_size_t), _vp]),
     "yume_pdq_cuda_synth_frames": (C.c_int, [C.c_int, _vp, C.c_size_t, C.c_uint64, C.c_uint64, C.c_int, _vp]),
@@ -485,11 +487,12 @@ class CudaMatcher:
             return out[: k.value].copy()
 
     def find_device(self, needles_dev, q: int, out_dev, cap: int, count_dev, algo: int = ALGO_AUTO,
-                    stream=None):
-        """Asynchronous device-side scan (torch CUDA tensors or raw device pointers)."""
-        _check(lib.yume_pdq_cuda_matcher_find_device(self.haystack._h, _ptr(needles_dev), q,
-                                                     self.threshold, _ptr(out_dev), cap, _ptr(count_dev),
-                                                     algo, _stream(stream or self.stream)),
+                    stream=None, needle_base: int = 0):
+        """Asynchronous device-side scan (torch CUDA tensors or raw device pointers); ``needle_base`` is
+        added to the reported needle indices (chunked callers)."""
+        _check(lib.yume_pdq_cuda_matcher_find_device_base(self.haystack._h, _ptr(needles_dev), q,
+                                                          self.threshold, _ptr(out_dev), cap, _ptr(count_dev),
+                                                          algo, needle_base, _stream(stream or self.stream)),
                "matcher_find_device")
 
 

@@ -807,6 +807,19 @@ int yume_pdq_cuda_matcher_find_device(YumePDQ_CudaDb *db, const uint8_t *needles
                         count_dev, nullptr, MODE_LIST, algo, db->sm_count, (cudaStream_t)stream);
 }
 
+int yume_pdq_cuda_matcher_find_device_base(YumePDQ_CudaDb *db, const uint8_t *needles_dev, size_t q,
+                                           uint32_t threshold, YumePDQ_Match *out_dev, uint32_t cap,
+                                           uint32_t *count_dev, int algo, uint32_t needle_base, void *stream)
+{
+    if (!db || !needles_dev || !count_dev || q == 0 || (cap && !out_dev))
+        return YUME_PDQ_CUDA_E_INVALID;
+    int rc = ensure_device(db->device);
+    if (rc)
+        return rc;
+    return launch_match(db->rows, db->n_rows, db->offset, needles_dev, q, threshold, out_dev, cap,
+                        count_dev, nullptr, MODE_LIST, algo, db->sm_count, (cudaStream_t)stream, needle_base);
+}
+
 int yume_pdq_cuda_screen_batch(YumePDQ_CudaDb *db, const float *frames, size_t n, uint32_t threshold,
                                uint8_t *hashes, float *quality, YumePDQ_Match *out, size_t cap,
                                size_t *n_found, void *stream)

@@ -429,9 +429,13 @@ match_tensor4_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint
                     if (lane == 0)
                         bar_arrive_addr(dempty + 8 * acc);
                     if (batch_any(v, mb)) {
-                        const uint32_t needle = (mt / T4_NB) * T4_M + quad * 32 + lane;
+                        // rare path: indices are rebuilt from opaque copies of the loop counters so that the
+                        // compiler does not carry 64-bit row arithmetic through the hot loop
+                        uint32_t si_ = si, mt_ = mt;
+                        asm volatile("" : "+r"(si_), "+r"(mt_));
+                        const uint32_t needle = (mt_ / T4_NB) * T4_M + quad * 32 + lane;
                         if (needle < q) {
-                            const uint64_t st = blockIdx.x + (uint64_t)si * gridDim.x;
+                            const uint64_t st = blockIdx.x + (uint64_t)si_ * gridDim.x;
                             report_hits(v, min_bits, st * T4_ROWS + acc * T4_N + part * T4_EB, n_rows, needle, sink);
                         }
                     }

@@ -116,6 +116,75 @@ class ShardedMatcher:
         import torch
         return gather_match_lists(local, cap, device=torch.device("cuda", self.device), group=self.group)
 
+    def screen(self, local_frames, hashes_out=None, cap: int = 1 << 16, chunk: int = 128) -> np.ndarray:
+        """Pipelined multi-GPU hash + match (BASELINE config 4: video screening against a sharded DB).
+
+        ``local_frames``: this rank's [n_local, 512, 512] f32 frames -- a (pinned) host numpy array /
+        CPU tensor, or a CUDA tensor; every rank passes the same n_local.  Per chunk of ``chunk`` frames:
+        [H2D of chunk i+1 on a copy stream] || [hash chunk i -> all-gather its 8 * chunk needles over
+        NCCL -> match the world * 8 * chunk gathered needles against this rank's row shard].  One host
+        synchronisation at the end, then the gather + merge of the match lists.  Returns, on every rank,
+        all matches sorted by (row, needle) with needle = 8 * global_frame + dihedral and
+        global_frame = rank * n_local + local index.  ``hashes_out`` ([n_local, 8, 32] uint8 CUDA tensor)
+        receives this rank's hashes if given."""
+        import torch
+        import torch.distributed as dist
+        from . import CudaKernel, MATCH_DTYPE as MD
+        if self.world == 1:
+            return self.matcher.screen(local_frames, hashes=hashes_out, cap=cap)
+        dev = torch.device("cuda", self.device)
+        n = int(local_frames.shape[0])
+        W = self.world
+        on_host = not (hasattr(local_frames, "is_cuda") and local_frames.is_cuda)
+        if on_host and not hasattr(local_frames, "is_cuda"):
+            local_frames = torch.from_numpy(np.ascontiguousarray(local_frames, dtype=np.float32))
+        kern = CudaKernel(self.device)
+        hashes = hashes_out if hashes_out is not None else torch.empty((n, 8, 32), dtype=torch.uint8, device=dev)
+        gath = [torch.empty((W * chunk * 8, 32), dtype=torch.uint8, device=dev) for _ in range(2)]
+        out = torch.zeros((cap, 16), dtype=torch.uint8, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        main = torch.cuda.current_stream(dev)
+        if on_host:
+            copy = torch.cuda.Stream(dev)
+            bufs = [torch.empty((chunk, 512, 512), dtype=torch.float32, device=dev) for _ in range(2)]
+            ev_copied = [torch.cuda.Event() for _ in range(2)]
+            ev_done = [torch.cuda.Event() for _ in range(2)]
+        n_chunks = (n + chunk - 1) // chunk
+        for c in range(n_chunks):
+            f0, k = c * chunk, min(chunk, n - c * chunk)
+            b = c & 1
+            if on_host:
+                with torch.cuda.stream(copy):
+                    if c >= 2:
+                        copy.wait_event(ev_done[b])
+                    bufs[b][:k].copy_(local_frames[f0:f0 + k], non_blocking=True)
+                    ev_copied[b].record(copy)
+                main.wait_event(ev_copied[b])
+                src = bufs[b][:k]
+            else:
+                src = local_frames[f0:f0 + k]
+            kern.hash_batch(src, want_quality=False, want_thresholds=False, out={"hashes": hashes[f0:f0 + k]})
+            if on_host:
+                ev_done[b].record(main)
+            g = gath[b][: W * k * 8]
+            dist.all_gather_into_tensor(g, hashes[f0:f0 + k].reshape(-1, 32), group=self.group)
+            # chunk-local needle index p = r * 8k + i; rebased below to 8 * (r * n + f0) + i
+            self.matcher.find_device(g, W * k * 8, out, cap, cnt, needle_base=c * W * chunk * 8)
+        # every rank must take the same decision about a retry (the retry runs collectives): agree on the
+        # largest per-rank match count
+        worst = cnt.to(torch.int64)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=self.group)
+        total, worst = int(cnt.item()), int(worst.item())
+        if worst > cap:
+            return self.screen(local_frames, hashes_out=hashes_out, cap=worst, chunk=chunk)
+        local = out[:total].cpu().numpy().view(MD).reshape(-1).copy()
+        cidx = local["needle"] // (W * chunk * 8)
+        p = local["needle"] % (W * chunk * 8)
+        k8 = np.minimum(chunk, n - cidx * chunk).astype(np.int64) * 8
+        r, i = p // k8, p % k8
+        local["needle"] = ((r * n + cidx * chunk) * 8 + i).astype(np.uint32)
+        return gather_match_lists(local, cap, device=dev, group=self.group)
+
     def scan(self, local_needles) -> bool:
         if self.world == 1:
             return self.matcher.scan(local_needles)
