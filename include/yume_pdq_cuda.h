@@ -108,6 +108,33 @@ extern const uint32_t YUME_PDQ_CUDA_DIHEDRAL_ORDER[8];
 int yume_pdq_cuda_hash_batch(int device, const float *frames, size_t n, uint8_t *hashes,
                              float *quality, float *thresholds, float *pdqf, void *stream);
 
+/* ---- pixel formats: the input conversion fused into the hasher ----
+ * The reference CLI converts every input row to f32 luma before hash_get_threshold
+ * (src/main.rs:486-608): LUMA8 by `as f32` (main.rs:508-510), RGB8 / RGBA8 through
+ * Kernel::cvt_rgb8_to_luma8f / cvt_rgba8_to_luma8f (src/kernel/mod.rs:303-340) with the ITU
+ * BT.601 table (src/kernel/constants.rs:23).  Here the conversion happens inside the window
+ * load of the hash kernel, so an 8-bit frame crosses PCIe and HBM once, as bytes.
+ * A frame is 512 x 512 pixels, row-major, tightly packed (RGB8: 3 bytes per pixel R,G,B;
+ * RGBA8: R,G,B,A with A ignored).  Results equal cvt-to-f32 followed by the f32 path, bit for bit.
+ * YUME_PDQ_CUDA_PIXEL_FMA (RGB8/RGBA8 only) selects the rounding of the AVX2 override
+ * (mul, fmadd, fmadd; src/kernel/x86.rs:686-753) instead of the trait default. */
+#define YUME_PDQ_CUDA_PIXEL_F32 0
+#define YUME_PDQ_CUDA_PIXEL_LUMA8 1
+#define YUME_PDQ_CUDA_PIXEL_RGB8 2
+#define YUME_PDQ_CUDA_PIXEL_RGBA8 3
+#define YUME_PDQ_CUDA_PIXEL_FMA 0x100
+/* bytes of one frame in pixel_format (0 = invalid format) */
+size_t yume_pdq_cuda_frame_bytes(int pixel_format);
+/* yume_pdq_cuda_hash_batch for frames in any pixel format (device pointers 16-byte aligned) */
+int yume_pdq_cuda_hash_batch_pixels(int device, const void *frames, int pixel_format, size_t n,
+                                    uint8_t *hashes, float *quality, float *thresholds, float *pdqf,
+                                    void *stream);
+/* Kernel::cvt_rgb8_to_luma8f / cvt_rgba8_to_luma8f (mod.rs:303-340) and the LUMA8 cast on their
+ * own, batched over n_pixels pixels (any number of rows): pixels -> out[n_pixels] f32.
+ * coeff = {R, G, B} like the trait's const generics, NULL = the ITU table. */
+int yume_pdq_cuda_cvt_to_luma8f(int device, const void *pixels, int pixel_format, size_t n_pixels,
+                                const float *coeff, float *out, void *stream);
+
 /* ---- hasher: the stages of the `Kernel` trait, batched over n ----
  * Kernel::jarosz_compress (mod.rs:644-666): frames n x 512 x 512 -> buf1 n x 128 x 128
  * (127 x 127 valid, padding written as zero, cf. x86.rs:756-757). */
@@ -223,11 +250,20 @@ int yume_pdq_cuda_screen_batch(YumePDQ_CudaDb *db, const float *frames, size_t n
                                uint8_t *hashes, float *quality, YumePDQ_Match *out, size_t cap,
                                size_t *n_found, void *stream);
 
+/* yume_pdq_cuda_screen_batch for frames in any pixel format: with LUMA8 frames a step moves
+ * 256 KiB per frame over PCIe instead of 1 MiB. */
+int yume_pdq_cuda_screen_batch_pixels(YumePDQ_CudaDb *db, const void *frames, int pixel_format, size_t n,
+                                      uint32_t threshold, uint8_t *hashes, float *quality,
+                                      YumePDQ_Match *out, size_t cap, size_t *n_found, void *stream);
+
 /* ---- synthetic inputs (device-side generators shared with the oracle) ----
  * frames_dev n x 512 x 512 f32 DEVICE pointer. kind 0: uniform 8-bit noise;
  * kind 1: smooth integer triangle waves + noise (see oracle/pdq_oracle.c). */
 int yume_pdq_cuda_synth_frames(int device, float *frames_dev, size_t n, uint64_t first_frame,
                                uint64_t seed, int kind, void *stream);
+/* 8-bit frames (LUMA8 / RGB8 / RGBA8), n x 512 x 512 x channels DEVICE bytes */
+int yume_pdq_cuda_synth_pixels(int device, void *frames_dev, int pixel_format, size_t n,
+                               uint64_t first_frame, uint64_t seed, void *stream);
 int yume_pdq_cuda_synth_rows(int device, uint8_t *rows_dev, size_t n_rows, uint64_t first_row,
                              uint64_t seed, void *stream);
 

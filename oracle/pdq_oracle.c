@@ -446,3 +446,72 @@ API void oracle_synth_frames(float *frames, size_t n_frames, uint64_t first_fram
                 frames[(f * 512 + y) * 512 + x] =
                     oracle_synth_pixel(seed, first_frame + f, y, x, kind);
 }
+
+/* 8-bit frames for the pixel-format paths (restated by synth_pixels_kernel in synth.cu): channel c of pixel
+ * (y, x) = (3 * acc_c + noise_c) >> 6 with the triangle waves of kind 1 weighted 1 + ((t + c) & 3);
+ * alpha = a noise byte.  channels = 1 (LUMA8), 3 (RGB8) or 4 (RGBA8). */
+API void oracle_synth_pixels(uint8_t *frames, size_t n_frames, uint64_t first_frame, uint64_t seed,
+                             int channels)
+{
+    for (size_t f = 0; f < n_frames; f++) {
+        uint64_t frame = first_frame + f;
+        uint64_t g = splitmix64_mix(seed ^ splitmix64_mix(frame + 0x1234u));
+        for (uint32_t y = 0; y < 512; y++)
+            for (uint32_t x = 0; x < 512; x++) {
+                uint64_t h = splitmix64_mix(seed + (frame << 18) + ((uint64_t)y << 9) + x);
+                uint32_t tri[4];
+                for (uint32_t t = 0; t < 4; t++) {
+                    uint32_t a = (uint32_t)(g >> (12 * t)) & 7u;
+                    uint32_t b = (uint32_t)(g >> (12 * t + 3)) & 7u;
+                    uint32_t c = (uint32_t)(g >> (12 * t + 6)) & 63u;
+                    uint32_t ph = (2u * a * x + 2u * b * y + 16u * c) & 1023u;
+                    tri[t] = ph < 512u ? ph : 1024u - ph;
+                }
+                uint8_t *px = frames + ((f * 512 + y) * 512 + x) * (size_t)channels;
+                for (int c = 0; c < channels; c++) {
+                    if (c == 3) {
+                        px[c] = (uint8_t)(h >> 24);
+                        break;
+                    }
+                    uint32_t acc = 0;
+                    for (uint32_t t = 0; t < 4; t++)
+                        acc += tri[t] * (1u + ((t + (uint32_t)c) & 3u));
+                    px[c] = (uint8_t)((3u * acc + ((uint32_t)(h >> (56 - 8 * c)) & 0xffu)) >> 6);
+                }
+            }
+    }
+}
+
+/* ------------------------------------------------------------------ f2 --
+ * Input conversion, the step before hash_get_threshold in the reference CLI (main.rs:486-608).
+ * LUMA8: `row_buf[j] as f32` (main.rs:508-510).
+ * Kernel::cvt_rgb8_to_luma8f / cvt_rgba8_to_luma8f, trait default (src/kernel/mod.rs:303-340):
+ *   luma = cr * r + cg * g + cb * b, separate f32 multiplies and adds, left to right; alpha ignored.
+ * fma != 0 restates the AVX2 override of the RGBA8 conversion (src/kernel/x86.rs:686-753):
+ *   v = r * cr;  v = fma(g, cg, v);  v = fma(b, cb, v).
+ * Coefficients are passed as f32 bit patterns like the trait's const generics; the CLI always uses
+ * RGB8_TO_LUMA8_TABLE_ITU = [0.299, 0.587, 0.114] (src/kernel/constants.rs:23). */
+API const float ORACLE_RGB8_TO_LUMA8_TABLE_ITU[3] = {0.299f, 0.587f, 0.114f};
+
+API void oracle_cvt_to_luma8f(const uint8_t *in, int channels, size_t n_pixels, uint32_t r_bits,
+                              uint32_t g_bits, uint32_t b_bits, int fma, float *out)
+{
+    const float cr = lut_f32(r_bits), cg = lut_f32(g_bits), cb = lut_f32(b_bits);
+    for (size_t i = 0; i < n_pixels; i++) {
+        const uint8_t *px = in + i * (size_t)channels;
+        if (channels == 1) {
+            out[i] = (float)px[0];
+            continue;
+        }
+        float r = (float)px[0], g = (float)px[1], b = (float)px[2];
+        if (fma) {
+            float v = r * cr;
+            v = fmaf(g, cg, v);
+            v = fmaf(b, cb, v);
+            out[i] = v;
+        } else {
+            float t0 = cr * r, t1 = cg * g, t2 = cb * b;
+            out[i] = (t0 + t1) + t2;
+        }
+    }
+}

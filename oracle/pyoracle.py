@@ -77,6 +77,11 @@ class Oracle:
         L.oracle_matcher_find_min.restype = C.c_uint64
         L.oracle_synth_db.argtypes = [_u8p, C.c_size_t, C.c_uint64, C.c_uint64]
         L.oracle_synth_frames.argtypes = [_f32p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_int]
+        L.oracle_synth_pixels.argtypes = [_u8p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_int]
+        L.oracle_cvt_to_luma8f.argtypes = [_u8p, C.c_int, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32,
+                                           C.c_int, _f32p]
+        self.luma_table_itu = np.array(list((C.c_float * 3).in_dll(L, "ORACLE_RGB8_TO_LUMA8_TABLE_ITU")),
+                                       dtype=np.float32)
         self.dihedral_order = list((C.c_uint32 * 8).in_dll(L, "ORACLE_DIHEDRAL_ORDER"))
 
     # ---- hashing ---------------------------------------------------------
@@ -136,6 +141,18 @@ class Oracle:
 
     def negate_off_diagonals(self, pdqf):
         return self._inplace("oracle_negate_off_diagonals", pdqf)
+
+    def cvt_to_luma8f(self, pixels: np.ndarray, channels: int, coeff=None, fma: bool = False) -> np.ndarray:
+        """u8 [..., channels] (channels 3/4) or u8 [...] (channels 1) -> f32 luma, mod.rs:303-340 /
+        main.rs:508-510; fma=True restates the AVX2 override x86.rs:686-753."""
+        pixels = np.ascontiguousarray(pixels, dtype=np.uint8)
+        shape = pixels.shape[:-1] if channels > 1 else pixels.shape
+        cf = self.luma_table_itu if coeff is None else np.asarray(coeff, dtype=np.float32)
+        bits = [int(b) for b in cf.view(np.uint32)]
+        out = np.zeros(shape, dtype=np.float32)
+        self.lib.oracle_cvt_to_luma8f(_bp(pixels), channels, out.size, bits[0], bits[1], bits[2], int(fma),
+                                      _fp(out))
+        return out
 
     def hash_get_threshold(self, frame):
         """-> (quality, threshold, hash[32] u8, pdqf[16,16]) like lib.rs:427-455."""
@@ -212,6 +229,13 @@ class Oracle:
                      kind: int = 1):
         frames = np.zeros((n, 512, 512), dtype=np.float32)
         self.lib.oracle_synth_frames(_fp(frames), n, first_frame, seed, kind)
+        return frames
+
+
+    def synth_pixels(self, n: int, channels: int, first_frame: int = 0, seed: int = 0x79756D652D706471):
+        shape = (n, 512, 512) if channels == 1 else (n, 512, 512, channels)
+        frames = np.zeros(shape, dtype=np.uint8)
+        self.lib.oracle_synth_pixels(_bp(frames), n, first_frame, seed, channels)
         return frames
 
 

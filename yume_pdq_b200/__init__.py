@@ -36,6 +36,10 @@ OP_NEGATE_ALT_ROWS_TRUE = 3
 OP_NEGATE_ALT_ROWS_FALSE = 4
 OP_NEGATE_OFF_DIAGONALS = 5
 
+PIXEL_F32, PIXEL_LUMA8, PIXEL_RGB8, PIXEL_RGBA8, PIXEL_FMA = 0, 1, 2, 3, 0x100
+# RGB8_TO_LUMA8_TABLE_ITU, src/kernel/constants.rs:23
+RGB8_TO_LUMA8_TABLE_ITU = (0.299, 0.587, 0.114)
+
 E_INVALID, E_NO_DEVICE, E_CAPACITY, E_NOMEM = -1, -2, -3, -4
 
 
@@ -72,6 +76,9 @@ SIGNATURES = {
     "yume_pdq_cuda_matcher_ident": (C.c_char_p, []),
     "yume_pdq_cuda_launch_count": (C.c_uint64, []),
     "yume_pdq_cuda_hash_batch": (C.c_int, [C.c_int, _vp, C.c_size_t, _vp, _vp, _vp, _vp, _vp]),
+    "yume_pdq_cuda_frame_bytes": (C.c_size_t, [C.c_int]),
+    "yume_pdq_cuda_hash_batch_pixels": (C.c_int, [C.c_int, _vp, C.c_int, C.c_size_t, _vp, _vp, _vp, _vp, _vp]),
+    "yume_pdq_cuda_cvt_to_luma8f": (C.c_int, [C.c_int, _vp, C.c_int, C.c_size_t, _vp, _vp, _vp]),
     "yume_pdq_cuda_jarosz_compress": (C.c_int, [C.c_int, _vp, C.c_size_t, _vp, _vp]),
     "yume_pdq_cuda_dct2d": (C.c_int, [C.c_int, _vp, C.c_size_t, _vp, _vp]),
     "yume_pdq_cuda_sum_of_gradients": (C.c_int, [C.c_int, _vp, C.c_size_t, _vp, _vp, _vp]),
@@ -98,6 +105,9 @@ SIGNATURES = {
                                                          _vp, C.c_int, C.c_uint32, _vp]),
     "yume_pdq_cuda_screen_batch": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _vp, _vp, _vp, C.c_size_t,
                                              C.POINTER(C.c_size_t), _vp]),
+    "yume_pdq_cuda_screen_batch_pixels": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t, C.c_uint32, _vp, _vp, _vp,
+                                                    C.c_size_t, C.POINTER(C.c_size_t), _vp]),
+    "yume_pdq_cuda_synth_pixels": (C.c_int, [C.c_int, _vp, C.c_int, C.c_size_t, C.c_uint64, C.c_uint64, _vp]),
     "yume_pdq_cuda_synth_frames": (C.c_int, [C.c_int, _vp, C.c_size_t, C.c_uint64, C.c_uint64, C.c_int, _vp]),
     "yume_pdq_cuda_synth_rows": (C.c_int, [C.c_int, _vp, C.c_size_t, C.c_uint64, C.c_uint64, _vp]),
 }
@@ -222,6 +232,31 @@ class CudaKernel:
         import torch
         return torch.empty(shape, dtype=getattr(torch, np.dtype(dtype).name), device=like.device)
 
+    # input conversion (mod.rs:303-340); rows [..., 3] / [..., 4] u8 -> f32 luma of the leading shape
+    def _cvt(self, pixels, fmt, channels, coeff, fma):
+        if channels > 1 and pixels.shape[-1] != channels:
+            raise ValueError(f"last dimension must be {channels}")
+        shape = tuple(pixels.shape[:-1]) if channels > 1 else tuple(pixels.shape)
+        n_pixels = int(np.prod(shape)) if shape else 1
+        out = self._out(pixels, shape, np.float32)
+        cf = None if coeff is None else (C.c_float * 3)(*coeff)
+        _check(lib.yume_pdq_cuda_cvt_to_luma8f(self.device, _ptr(pixels), fmt | (PIXEL_FMA if fma else 0),
+                                               n_pixels, cf, _ptr(out), _stream(self.stream)), "cvt_to_luma8f")
+        return out
+
+    def cvt_rgb8_to_luma8f(self, rows, coeff=None, fma=False):
+        """Kernel::cvt_rgb8_to_luma8f (mod.rs:303-321): u8 [..., 3] -> f32 [...]; coeff = (R, G, B) like the
+        trait's const generics (default: the ITU table); fma=True: AVX2 rounding (x86.rs:686-753)."""
+        return self._cvt(rows, PIXEL_RGB8, 3, coeff, fma)
+
+    def cvt_rgba8_to_luma8f(self, rows, coeff=None, fma=False):
+        """Kernel::cvt_rgba8_to_luma8f (mod.rs:324-340): u8 [..., 4] -> f32 [...], alpha ignored."""
+        return self._cvt(rows, PIXEL_RGBA8, 4, coeff, fma)
+
+    def cvt_luma8_to_luma8f(self, rows):
+        """`row_buf[j] as f32` of the CLI's LUMA8 input (main.rs:508-510)."""
+        return self._cvt(rows, PIXEL_LUMA8, 1, None, False)
+
     def jarosz_compress(self, frames, out=None):
         n = frames.shape[0]
         out = self._out(frames, (n, 128, 128), np.float32) if out is None else out
@@ -277,10 +312,13 @@ class CudaKernel:
         return self._transform(pdqf, OP_NEGATE_OFF_DIAGONALS)
 
     # fused hot path
-    def hash_batch(self, frames, want_quality=True, want_thresholds=True, want_pdqf=False, out=None):
-        """frames [n,512,512] f32 -> dict(hashes [n,8,32] u8, quality [n,8], thresholds [n,8],
-        pdqf [n,16,16]) in DIHEDRAL_ORDER."""
+    def hash_batch(self, frames, want_quality=True, want_thresholds=True, want_pdqf=False, out=None,
+                   pixel_format: int = PIXEL_F32):
+        """frames [n,512,512] f32 (or u8 [n,512,512] / [n,512,512,3] / [n,512,512,4] with the matching
+        ``pixel_format``) -> dict(hashes [n,8,32] u8, quality [n,8], thresholds [n,8], pdqf [n,16,16])
+        in DIHEDRAL_ORDER."""
         n = frames.shape[0]
+        _check_frames(frames, pixel_format)
         out = out or {}
         hashes = out.get("hashes")
         if hashes is None:
@@ -294,8 +332,9 @@ class CudaKernel:
         pdqf = out.get("pdqf")
         if pdqf is None and want_pdqf:
             pdqf = self._out(frames, (n, 16, 16), np.float32)
-        _check(lib.yume_pdq_cuda_hash_batch(self.device, _ptr(frames), n, _ptr(hashes), _ptr(quality),
-                                            _ptr(thr), _ptr(pdqf), _stream(self.stream)), "hash_batch")
+        _check(lib.yume_pdq_cuda_hash_batch_pixels(self.device, _ptr(frames), pixel_format, n, _ptr(hashes),
+                                                   _ptr(quality), _ptr(thr), _ptr(pdqf), _stream(self.stream)),
+               "hash_batch")
         return {"hashes": hashes, "quality": quality, "thresholds": thr, "pdqf": pdqf}
 
     def dihedrals_batch(self, pdqf, thr0):
@@ -307,6 +346,17 @@ class CudaKernel:
                                                  _ptr(quality), _ptr(thr), _stream(self.stream)),
                "dihedrals_batch")
         return {"hashes": hashes, "quality": quality, "thresholds": thr}
+
+
+def _check_frames(frames, pixel_format: int) -> None:
+    """The byte size of ``frames`` must be n frames of ``pixel_format`` (a wrong format would read out of bounds)."""
+    fb = int(lib.yume_pdq_cuda_frame_bytes(pixel_format))
+    if fb == 0:
+        raise ValueError(f"unknown pixel format {pixel_format:#x}")
+    nbytes = frames.nbytes if isinstance(frames, np.ndarray) else frames.numel() * frames.element_size()
+    if nbytes != int(frames.shape[0]) * fb:
+        raise ValueError(f"frames hold {nbytes} bytes, expected {frames.shape[0]} x {fb} for pixel format "
+                         f"{pixel_format:#x}")
 
 
 def smart_kernel(device: int = 0) -> CudaKernel:
@@ -468,18 +518,19 @@ class CudaMatcher:
             return None
         return int(k.value) // q, int(k.value) % q
 
-    def screen(self, frames, hashes=None, quality=None, cap: int = 65536):
-        """Hash ``frames`` (n x 512 x 512 f32, numpy or torch CUDA) and match all 8 n dihedral hashes
+    def screen(self, frames, hashes=None, quality=None, cap: int = 65536, pixel_format: int = PIXEL_F32):
+        """Hash ``frames`` (n x 512 x 512 f32 -- or 8-bit frames with ``pixel_format`` --, numpy or torch CUDA) and match all 8 n dihedral hashes
         against the haystack in one pipelined call (examples/end_to_end.rs:224-256 for a batch).
         Returns the matches (needle = 8 * frame + dihedral) sorted by (row, needle); fills ``hashes``
         (n x 8 x 32) / ``quality`` (n x 8) when given."""
         n = int(frames.shape[0])
+        _check_frames(frames, pixel_format)
         while True:
             out = np.zeros(max(cap, 1), dtype=MATCH_DTYPE)
             k = C.c_size_t(0)
-            rc = lib.yume_pdq_cuda_screen_batch(self.haystack._h, _ptr(frames), n, self.threshold,
-                                                _ptr(hashes), _ptr(quality), _ptr(out), cap, C.byref(k),
-                                                _stream(self.stream))
+            rc = lib.yume_pdq_cuda_screen_batch_pixels(self.haystack._h, _ptr(frames), pixel_format, n,
+                                                       self.threshold, _ptr(hashes), _ptr(quality), _ptr(out),
+                                                       cap, C.byref(k), _stream(self.stream))
             if rc == E_CAPACITY:
                 cap = int(k.value)
                 continue
@@ -500,6 +551,12 @@ def synth_frames(frames_dev, n: int, first_frame: int = 0, seed: int = 0x79756D6
                  device: int = 0, stream=None):
     _check(lib.yume_pdq_cuda_synth_frames(device, _ptr(frames_dev), n, first_frame, seed, kind,
                                           _stream(stream)), "synth_frames")
+
+
+def synth_pixels(frames_dev, n: int, pixel_format: int, first_frame: int = 0, seed: int = 0x79756D652D706471,
+                 device: int = 0, stream=None):
+    _check(lib.yume_pdq_cuda_synth_pixels(device, _ptr(frames_dev), pixel_format, n, first_frame, seed,
+                                          _stream(stream)), "synth_pixels")
 
 
 def synth_rows(rows_dev, n_rows: int, first_row: int = 0, seed: int = 0x79756D652D706471, device: int = 0,

@@ -332,14 +332,16 @@ namespace {
 // kernel of each chunk has been enqueued -- yume_pdq_cuda_screen_batch enqueues that chunk's match there.
 // d_in: device scratch for 2 * chunk frames (host frames only).
 template <class F>
-int hash_chunks(int device, const float *frames, size_t n, uint8_t *d_hashes, float *d_quality, float *d_thr,
-                float *d_pdqf, cudaStream_t s, size_t chunk, float *d_in0, F after_chunk)
+int hash_chunks(int device, const void *frames_v, int fmt, size_t n, uint8_t *d_hashes, float *d_quality,
+                float *d_thr, float *d_pdqf, cudaStream_t s, size_t chunk, void *d_in0, F after_chunk)
 {
+    const uint8_t *frames = static_cast<const uint8_t *>(frames_v);
+    const size_t fb = frame_bytes(fmt);
     if (is_device_ptr(frames)) {
-        int rc = launch_hash_batch(frames, n, d_hashes, d_quality, d_thr, d_pdqf, s);
+        int rc = launch_hash_batch(frames, fmt, n, d_hashes, d_quality, d_thr, d_pdqf, s);
         return rc ? rc : after_chunk((size_t)0, n);
     }
-    float *d_in[2] = {d_in0, d_in0 + chunk * (512 * 512)};
+    uint8_t *d_in[2] = {static_cast<uint8_t *>(d_in0), static_cast<uint8_t *>(d_in0) + chunk * fb};
     static thread_local cudaStream_t copy_stream = nullptr;
     static thread_local cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     static thread_local int ev_dev = -1;
@@ -360,11 +362,10 @@ int hash_chunks(int device, const float *frames, size_t n, uint8_t *d_hashes, fl
         const size_t cnt = std::min(chunk, n - f0);
         if (ci >= 2)
             YPDQ_CUDA_TRY(cudaStreamWaitEvent(copy_stream, ev_done[b], 0));
-        YPDQ_CUDA_TRY(cudaMemcpyAsync(d_in[b], frames + f0 * (512 * 512), cnt * (size_t)(512 * 512 * 4),
-                                      cudaMemcpyHostToDevice, copy_stream));
+        YPDQ_CUDA_TRY(cudaMemcpyAsync(d_in[b], frames + f0 * fb, cnt * fb, cudaMemcpyHostToDevice, copy_stream));
         YPDQ_CUDA_TRY(cudaEventRecord(ev_copied[b], copy_stream));
         YPDQ_CUDA_TRY(cudaStreamWaitEvent(s, ev_copied[b], 0));
-        int rc = launch_hash_batch(d_in[b], cnt, d_hashes + f0 * 256, d_quality ? d_quality + f0 * 8 : nullptr,
+        int rc = launch_hash_batch(d_in[b], fmt, cnt, d_hashes + f0 * 256, d_quality ? d_quality + f0 * 8 : nullptr,
                                    d_thr ? d_thr + f0 * 8 : nullptr, d_pdqf ? d_pdqf + f0 * 256 : nullptr, s);
         if (rc)
             return rc;
@@ -380,9 +381,22 @@ int hash_chunks(int device, const float *frames, size_t n, uint8_t *d_hashes, fl
 
 extern "C" {
 
+size_t yume_pdq_cuda_frame_bytes(int pixel_format) { return frame_bytes(pixel_format); }
+
 int yume_pdq_cuda_hash_batch(int device, const float *frames, size_t n, uint8_t *hashes,
                              float *quality, float *thresholds, float *pdqf, void *stream)
 {
+    return yume_pdq_cuda_hash_batch_pixels(device, frames, YUME_PDQ_CUDA_PIXEL_F32, n, hashes, quality,
+                                           thresholds, pdqf, stream);
+}
+
+int yume_pdq_cuda_hash_batch_pixels(int device, const void *frames, int pixel_format, size_t n,
+                                    uint8_t *hashes, float *quality, float *thresholds, float *pdqf,
+                                    void *stream)
+{
+    const size_t fb = frame_bytes(pixel_format);
+    if (!fb)
+        return YUME_PDQ_CUDA_E_INVALID;
     if (!frames || !hashes)
         return n == 0 ? 0 : YUME_PDQ_CUDA_E_INVALID;
     if (n == 0)
@@ -396,8 +410,8 @@ int yume_pdq_cuda_hash_batch(int device, const float *frames, size_t n, uint8_t 
     Scratch &so = tls_scratch(0);
     size_t out_need = host_bytes(hashes, n * 256) + host_bytes(quality, n * 32) +
                       host_bytes(thresholds, n * 32) + host_bytes(pdqf, n * 1024);
-    const size_t chunk = std::min<size_t>(n, 64);  // frames per H2D chunk (64 MiB)
-    size_t in_need = frames_on_host ? 2 * chunk * (size_t)(512 * 512 * 4) : 0;
+    const size_t chunk = std::min<size_t>(n, 64);  // frames per H2D chunk (64 MiB of f32)
+    size_t in_need = frames_on_host ? 2 * chunk * fb : 0;
     rc = so.reserve(device, out_need + in_need + 4096, 0);
     if (rc)
         return rc;
@@ -409,8 +423,8 @@ int yume_pdq_cuda_hash_batch(int device, const float *frames, size_t n, uint8_t 
     st.out(quality, n * 32, &d_quality);
     st.out(thresholds, n * 32, &d_thr);
     st.out(pdqf, n * 1024, &d_pdqf);
-    float *d_in = reinterpret_cast<float *>(st.base + align_up(st.off, 256));
-    rc = hash_chunks(device, frames, n, d_hashes, d_quality, d_thr, d_pdqf, s, chunk, d_in,
+    void *d_in = st.base + align_up(st.off, 256);
+    rc = hash_chunks(device, frames, pixel_format, n, d_hashes, d_quality, d_thr, d_pdqf, s, chunk, d_in,
                      [](size_t, size_t) { return 0; });
     if (rc)
         return rc;
@@ -448,6 +462,30 @@ int yume_pdq_cuda_jarosz_compress(int device, const float *frames, size_t n, flo
         return rc;
     st.out(buf1, n * 65536, &d_buf1);
     rc = launch_jarosz(d_frames, n, d_buf1, s);
+    return rc ? rc : st.finish();
+}
+
+int yume_pdq_cuda_cvt_to_luma8f(int device, const void *pixels, int pixel_format, size_t n_pixels,
+                                const float *coeff, float *out, void *stream)
+{
+    const int fmt = pixel_format & ~YUME_PDQ_CUDA_PIXEL_FMA;
+    const size_t bpp = fmt == YUME_PDQ_CUDA_PIXEL_LUMA8 ? 1 : fmt == YUME_PDQ_CUDA_PIXEL_RGB8 ? 3
+                       : fmt == YUME_PDQ_CUDA_PIXEL_RGBA8 ? 4 : 0;
+    if (!bpp || (fmt == YUME_PDQ_CUDA_PIXEL_LUMA8 && pixel_format != fmt))
+        return YUME_PDQ_CUDA_E_INVALID;
+    if (n_pixels == 0)
+        return 0;
+    if (!pixels || !out)
+        return YUME_PDQ_CUDA_E_INVALID;
+    const uint8_t *px = static_cast<const uint8_t *>(pixels);
+    STAGE_BEGIN(device, host_bytes(px, n_pixels * bpp) + host_bytes(out, n_pixels * 4));
+    const uint8_t *d_px;
+    float *d_out;
+    rc = st.in(px, n_pixels * bpp, &d_px);
+    if (rc)
+        return rc;
+    st.out(out, n_pixels * 4, &d_out);
+    rc = launch_cvt_luma8f(d_px, pixel_format, n_pixels, coeff, d_out, s);
     return rc ? rc : st.finish();
 }
 
@@ -824,7 +862,16 @@ int yume_pdq_cuda_screen_batch(YumePDQ_CudaDb *db, const float *frames, size_t n
                                uint8_t *hashes, float *quality, YumePDQ_Match *out, size_t cap,
                                size_t *n_found, void *stream)
 {
-    if (!db || !n_found || (cap && !out) || (n && !frames) || n > 0x1fffffffull)
+    return yume_pdq_cuda_screen_batch_pixels(db, frames, YUME_PDQ_CUDA_PIXEL_F32, n, threshold, hashes, quality,
+                                             out, cap, n_found, stream);
+}
+
+int yume_pdq_cuda_screen_batch_pixels(YumePDQ_CudaDb *db, const void *frames, int pixel_format, size_t n,
+                                      uint32_t threshold, uint8_t *hashes, float *quality,
+                                      YumePDQ_Match *out, size_t cap, size_t *n_found, void *stream)
+{
+    const size_t fb = frame_bytes(pixel_format);
+    if (!db || !fb || !n_found || (cap && !out) || (n && !frames) || n > 0x1fffffffull)
         return YUME_PDQ_CUDA_E_INVALID;
     *n_found = 0;
     if (n == 0)
@@ -837,11 +884,11 @@ int yume_pdq_cuda_screen_batch(YumePDQ_CudaDb *db, const float *frames, size_t n
     const int device = db->device;
     const bool frames_on_host = !is_device_ptr(frames);
     // device staging: hashes always (they are the needles), quality if wanted on the host, frame chunks
-    const size_t chunk = std::min<size_t>(n, 128);   // frames per pipeline step: 128 MiB H2D, 1024 needles
+    const size_t chunk = std::min<size_t>(n, 128);   // frames per pipeline step: 128 MiB of f32 H2D, 1024 needles
     Scratch &so = tls_scratch(1);
     const bool hashes_dev = hashes && is_device_ptr(hashes);
     const size_t need = (hashes_dev ? 0 : align_up(n * 256, 256)) + host_bytes(quality, n * 32) +
-                        (frames_on_host ? 2 * chunk * (size_t)(512 * 512 * 4) : 0) + 4096;
+                        (frames_on_host ? 2 * chunk * fb : 0) + 4096;
     rc = so.reserve(device, need, 0);
     if (rc)
         return rc;
@@ -855,7 +902,7 @@ int yume_pdq_cuda_screen_batch(YumePDQ_CudaDb *db, const float *frames, size_t n
         d_quality = reinterpret_cast<float *>(base + off);
         off += align_up(n * 32, 256);
     }
-    float *d_in = reinterpret_cast<float *>(base + off);
+    void *d_in = base + off;
 
     size_t list_cap = std::max<size_t>(cap, 1 << 16);
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -883,7 +930,8 @@ int yume_pdq_cuda_screen_batch(YumePDQ_CudaDb *db, const float *frames, size_t n
         };
         if (attempt == 0) {
             // pipeline: [H2D chunk i+1] || [hash chunk i -> match chunk i's 8 * cnt needles]
-            rc = hash_chunks(device, frames, n, d_hashes, d_quality, nullptr, nullptr, s, chunk, d_in, match_chunk);
+            rc = hash_chunks(device, frames, pixel_format, n, d_hashes, d_quality, nullptr, nullptr, s, chunk, d_in,
+                             match_chunk);
         } else {
             rc = match_chunk(0, n);   // list overflow: the hashes are resident, rescan with a larger list
         }
@@ -928,6 +976,18 @@ int yume_pdq_cuda_synth_frames(int device, float *frames_dev, size_t n, uint64_t
     if (rc)
         return rc;
     return launch_synth_frames(frames_dev, n, first_frame, seed, kind, (cudaStream_t)stream);
+}
+
+int yume_pdq_cuda_synth_pixels(int device, void *frames_dev, int pixel_format, size_t n, uint64_t first_frame,
+                               uint64_t seed, void *stream)
+{
+    if (n && !frames_dev)
+        return YUME_PDQ_CUDA_E_INVALID;
+    int rc = ensure_device(device);
+    if (rc)
+        return rc;
+    return launch_synth_pixels(static_cast<uint8_t *>(frames_dev), pixel_format, n, first_frame, seed,
+                               (cudaStream_t)stream);
 }
 
 int yume_pdq_cuda_synth_rows(int device, uint8_t *rows_dev, size_t n_rows, uint64_t first_row, uint64_t seed,

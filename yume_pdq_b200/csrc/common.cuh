@@ -44,8 +44,21 @@ inline bool is_device_ptr(const void *p)
 int ensure_device(int device);  // api.cu: validates + cudaSetDevice, returns 0 or error
 
 // ---- kernel launchers (defined in hasher.cu / matcher.cu / synth.cu) ----
-int launch_hash_batch(const float *frames, size_t n, uint8_t *hashes, float *quality,
+int launch_hash_batch(const void *frames, int pixel_format, size_t n, uint8_t *hashes, float *quality,
                       float *thresholds, float *pdqf, cudaStream_t s);
+int launch_cvt_luma8f(const void *pixels, int pixel_format, size_t n_pixels, const float *coeff, float *out,
+                      cudaStream_t s);
+// bytes of one 512 x 512 frame in `pixel_format`, 0 if the format is unknown
+inline size_t frame_bytes(int pixel_format)
+{
+    switch (pixel_format & ~YUME_PDQ_CUDA_PIXEL_FMA) {
+    case YUME_PDQ_CUDA_PIXEL_F32: return (pixel_format & YUME_PDQ_CUDA_PIXEL_FMA) ? 0 : (size_t)512 * 512 * 4;
+    case YUME_PDQ_CUDA_PIXEL_LUMA8: return (pixel_format & YUME_PDQ_CUDA_PIXEL_FMA) ? 0 : (size_t)512 * 512;
+    case YUME_PDQ_CUDA_PIXEL_RGB8: return (size_t)512 * 512 * 3;
+    case YUME_PDQ_CUDA_PIXEL_RGBA8: return (size_t)512 * 512 * 4;
+    default: return 0;
+    }
+}
 int launch_jarosz(const float *frames, size_t n, float *buf1, cudaStream_t s);
 int launch_dct2d(const float *buf1, size_t n, float *pdqf, cudaStream_t s);
 int launch_gradients(const float *pdqf, size_t n, float *gradient, float *quality, cudaStream_t s);
@@ -71,6 +84,8 @@ int launch_match_tensor4(const uint8_t *rows, size_t n_rows, uint64_t row_offset
                          unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base = 0);
 
 int launch_synth_frames(float *frames, size_t n, uint64_t first, uint64_t seed, int kind,
+                        cudaStream_t s);
+int launch_synth_pixels(uint8_t *frames, int pixel_format, size_t n, uint64_t first, uint64_t seed,
                         cudaStream_t s);
 int launch_synth_rows(uint8_t *rows, size_t n, uint64_t first, uint64_t seed, cudaStream_t s);
 

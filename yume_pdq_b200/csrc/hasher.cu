@@ -43,6 +43,7 @@ constexpr int PREFETCH_AHEAD = 8;
 
 __device__ __align__(16) float g_dt[127 * 16];          // D transposed, g_dt[k2*16 + k] = D[k][k2]
 __constant__ uint32_t c_tent_bits[49];    // W[di][dj], read as constant-bank operands
+__constant__ float c_luma[3] = {0.299f, 0.587f, 0.114f};  // RGB8_TO_LUMA8_TABLE_ITU, constants.rs:23
 
 struct __align__(16) HashSmem {
     float dt[127 * 16];        // D transposed: dt[k2*16 + k] = D[k][k2]
@@ -50,11 +51,6 @@ struct __align__(16) HashSmem {
     float p[256];              // PDQF
     float thr[4];              // medians of P, C.P, R.C.P, R.P
 };
-
-__device__ __forceinline__ float4 ldg4(const float *p)
-{
-    return __ldg(reinterpret_cast<const float4 *>(p));
-}
 
 __device__ __forceinline__ void prefetch_l2(const void *p, uint32_t bytes)
 {
@@ -67,18 +63,100 @@ __device__ __forceinline__ float tent_w(int di, int dj)
     return __uint_as_float(c_tent_bits[di * 7 + dj]);
 }
 
-// ---- window row DI (1..5): five taps in reference order (dj = 1..5); a = columns
-// 4j..4j+3, b = columns 4j+4..4j+7, the window is columns 4j+2..4j+6 ----
+// the five f32 luma taps of one window row: input columns 4j+2 .. 4j+6
+struct Win5 {
+    float v0, v1, v2, v3, v4;
+};
+
+// ---- window row DI (1..5): five taps in reference order (dj = 1..5) ----
 template <int DI>
-__device__ __forceinline__ float tent_row(float sum, const float4 &a, const float4 &b)
+__device__ __forceinline__ float tent_row(float sum, const Win5 &w)
 {
-    sum = __fadd_rn(sum, __fmul_rn(tent_w(DI, 1), a.z));
-    sum = __fadd_rn(sum, __fmul_rn(tent_w(DI, 2), a.w));
-    sum = __fadd_rn(sum, __fmul_rn(tent_w(DI, 3), b.x));
-    sum = __fadd_rn(sum, __fmul_rn(tent_w(DI, 4), b.y));
-    sum = __fadd_rn(sum, __fmul_rn(tent_w(DI, 5), b.z));
+    sum = __fadd_rn(sum, __fmul_rn(tent_w(DI, 1), w.v0));
+    sum = __fadd_rn(sum, __fmul_rn(tent_w(DI, 2), w.v1));
+    sum = __fadd_rn(sum, __fmul_rn(tent_w(DI, 3), w.v2));
+    sum = __fadd_rn(sum, __fmul_rn(tent_w(DI, 4), w.v3));
+    sum = __fadd_rn(sum, __fmul_rn(tent_w(DI, 5), w.v4));
     return sum;
 }
+
+// ---- pixel formats: the conversion the reference CLI applies to every input row
+// before hash_get_threshold (main.rs:486-608) is fused into the window load, so a u8 frame is read
+// from HBM once, as bytes.
+//   LUMA8  `row_buf[j] as f32`                                     main.rs:508-510
+//   RGB8   Kernel::cvt_rgb8_to_luma8f,  cr*r + cg*g + cb*b         mod.rs:303-321
+//   RGBA8  Kernel::cvt_rgba8_to_luma8f, alpha ignored              mod.rs:324-340
+// FMA = false is the trait default (separate multiplies and adds, left to right); FMA = true is
+// the rounding of the AVX2 override (mul, fmadd, fmadd; x86.rs:686-753).
+__device__ __forceinline__ float u8f(uint32_t w, int byte)
+{
+    return (float)((w >> (8 * byte)) & 0xffu);   // exact
+}
+
+template <bool FMA>
+__device__ __forceinline__ float luma_of(float r, float g, float b)
+{
+    if (FMA)
+        return __fmaf_rn(b, c_luma[2], __fmaf_rn(g, c_luma[1], __fmul_rn(r, c_luma[0])));
+    return __fadd_rn(__fadd_rn(__fmul_rn(c_luma[0], r), __fmul_rn(c_luma[1], g)), __fmul_rn(c_luma[2], b));
+}
+
+template <bool FMA>
+__device__ __forceinline__ float luma_rgba(uint32_t px)   // little-endian R, G, B, A
+{
+    return luma_of<FMA>(u8f(px, 0), u8f(px, 1), u8f(px, 2));
+}
+
+template <int FMT, bool FMA>
+struct Px;
+template <bool FMA>
+struct Px<YUME_PDQ_CUDA_PIXEL_F32, FMA> {
+    static constexpr int BPP = 4;
+    // p = row + 4j pixels; columns 4j..4j+7 in two 128-bit loads, the window is columns 4j+2..4j+6
+    static __device__ __forceinline__ Win5 load(const uint8_t *p)
+    {
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(p));
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+        return {a.z, a.w, b.x, b.y, b.z};
+    }
+};
+template <bool FMA>
+struct Px<YUME_PDQ_CUDA_PIXEL_LUMA8, FMA> {
+    static constexpr int BPP = 1;
+    static __device__ __forceinline__ Win5 load(const uint8_t *p)
+    {
+        const uint32_t a = __ldg(reinterpret_cast<const uint32_t *>(p));
+        const uint32_t b = __ldg(reinterpret_cast<const uint32_t *>(p) + 1);
+        return {u8f(a, 2), u8f(a, 3), u8f(b, 0), u8f(b, 1), u8f(b, 2)};
+    }
+};
+template <bool FMA>
+struct Px<YUME_PDQ_CUDA_PIXEL_RGB8, FMA> {
+    static constexpr int BPP = 3;
+    // pixels 4j+2..4j+6 are bytes 6..20 of p = row + 12j: words 1..5
+    static __device__ __forceinline__ Win5 load(const uint8_t *p)
+    {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(p);
+        const uint32_t w1 = __ldg(q + 1), w2 = __ldg(q + 2), w3 = __ldg(q + 3), w4 = __ldg(q + 4),
+                       w5 = __ldg(q + 5);
+        return {luma_of<FMA>(u8f(w1, 2), u8f(w1, 3), u8f(w2, 0)),
+                luma_of<FMA>(u8f(w2, 1), u8f(w2, 2), u8f(w2, 3)),
+                luma_of<FMA>(u8f(w3, 0), u8f(w3, 1), u8f(w3, 2)),
+                luma_of<FMA>(u8f(w3, 3), u8f(w4, 0), u8f(w4, 1)),
+                luma_of<FMA>(u8f(w4, 2), u8f(w4, 3), u8f(w5, 0))};
+    }
+};
+template <bool FMA>
+struct Px<YUME_PDQ_CUDA_PIXEL_RGBA8, FMA> {
+    static constexpr int BPP = 4;
+    static __device__ __forceinline__ Win5 load(const uint8_t *p)
+    {
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(p));
+        const uint4 b = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
+        return {luma_rgba<FMA>(a.z), luma_rgba<FMA>(a.w), luma_rgba<FMA>(b.x), luma_rgba<FMA>(b.y),
+                luma_rgba<FMA>(b.z)};
+    }
+};
 
 // value of dihedral d's PDQF at (i, j), from the untransformed PDQF in shared memory.
 // d: 0 P, 1 C.P, 2 R.C.P, 3 R.P, 4 P^T, 5 R.P^T, 6 C.R.P^T, 7 C.P^T with
@@ -245,11 +323,14 @@ __device__ __forceinline__ void rank1(float (&acc)[16][4], const float *dt_row, 
 }
 
 // ------------------------------------------------------------ fused kernel --
+template <int FMT, bool FMA>
 __global__ void __launch_bounds__(HT, 4)
-hash_fused_kernel(const float *__restrict__ frames, size_t n, uint8_t *__restrict__ hashes,
+hash_fused_kernel(const uint8_t *__restrict__ frames, size_t n, uint8_t *__restrict__ hashes,
                   float *__restrict__ quality, float *__restrict__ thresholds,
                   float *__restrict__ pdqf_out)
 {
+    using P = Px<FMT, FMA>;
+    constexpr size_t ROW = 512 * P::BPP;   // bytes per input row
     __shared__ HashSmem sm;
     const int tid = threadIdx.x;
     const int j = tid < 127 ? tid : 126;  // thread 127 shadows column 126 (never stored)
@@ -257,13 +338,13 @@ hash_fused_kernel(const float *__restrict__ frames, size_t n, uint8_t *__restric
     __syncthreads();
 
     for (size_t f = blockIdx.x; f < n; f += gridDim.x) {
-        const float *frame = frames + f * (512 * 512);
+        const uint8_t *frame = frames + f * (512 * ROW);
         // window of output (oi, j): rows 4oi+2 .. 4oi+6, columns 4j+2 .. 4j+6
-        const float *col = frame + 4 * j;
+        const uint8_t *col = frame + 4 * j * P::BPP;
         if (tid == 0) {
 #pragma unroll 1
             for (int a = 0; a < PREFETCH_AHEAD; a++)
-                prefetch_l2(frame + (size_t)(4 * a + 2) * 512, 4 * 2048);
+                prefetch_l2(frame + (size_t)(4 * a + 2) * ROW, 4 * ROW);
         }
         float acc[16][4];
 #pragma unroll
@@ -273,25 +354,24 @@ hash_fused_kernel(const float *__restrict__ frames, size_t n, uint8_t *__restric
                 acc[k][r] = 0.0f;
 
         // first window row (input row 2), carried between iterations afterwards
-        float4 ca = ldg4(col + 2 * 512), cb = ldg4(col + 2 * 512 + 4);
+        Win5 carry = P::load(col + 2 * ROW);
 
         auto one_row = [&](int oi, auto rtag) {
             constexpr int R = decltype(rtag)::value;  // oi & 3
-            const float *base = col + (size_t)(4 * oi + 3) * 512;
-            float4 a1 = ldg4(base), b1 = ldg4(base + 4);
-            float4 a2 = ldg4(base + 512), b2 = ldg4(base + 512 + 4);
-            float4 a3 = ldg4(base + 1024), b3 = ldg4(base + 1024 + 4);
-            float4 a4 = ldg4(base + 1536), b4 = ldg4(base + 1536 + 4);
+            const uint8_t *base = col + (size_t)(4 * oi + 3) * ROW;
+            const Win5 w1 = P::load(base);
+            const Win5 w2 = P::load(base + ROW);
+            const Win5 w3 = P::load(base + 2 * ROW);
+            const Win5 w4 = P::load(base + 3 * ROW);
             if (tid == 0 && oi + PREFETCH_AHEAD < 127)
-                prefetch_l2(frame + (size_t)(4 * (oi + PREFETCH_AHEAD) + 3) * 512, 4 * 2048);
+                prefetch_l2(frame + (size_t)(4 * (oi + PREFETCH_AHEAD) + 3) * ROW, 4 * ROW);
             float sum = 0.0f;
-            sum = tent_row<1>(sum, ca, cb);
-            sum = tent_row<2>(sum, a1, b1);
-            sum = tent_row<3>(sum, a2, b2);
-            sum = tent_row<4>(sum, a3, b3);
-            sum = tent_row<5>(sum, a4, b4);
-            ca = a4;
-            cb = b4;
+            sum = tent_row<1>(sum, carry);
+            sum = tent_row<2>(sum, w1);
+            sum = tent_row<3>(sum, w2);
+            sum = tent_row<4>(sum, w3);
+            sum = tent_row<5>(sum, w4);
+            carry = w4;
             rank1<R>(acc, sm.dt + oi * 16, sum);
         };
         using T0 = std::integral_constant<int, 0>;
@@ -340,13 +420,14 @@ jarosz_kernel(const float *__restrict__ frames, float *__restrict__ buf1)
         *out = 0.0f;  // zero padding of the 128x128 buffer (x86.rs:756-757, lib.rs:296-297)
         return;
     }
-    const float *base = frames + f * (512 * 512) + (size_t)(4 * oi + 2) * 512 + 4 * oj;
+    using P = Px<YUME_PDQ_CUDA_PIXEL_F32, false>;
+    const uint8_t *base = reinterpret_cast<const uint8_t *>(frames + f * (512 * 512) + (size_t)(4 * oi + 2) * 512 + 4 * oj);
     float sum = 0.0f;
-    sum = tent_row<1>(sum, ldg4(base), ldg4(base + 4));
-    sum = tent_row<2>(sum, ldg4(base + 512), ldg4(base + 512 + 4));
-    sum = tent_row<3>(sum, ldg4(base + 1024), ldg4(base + 1024 + 4));
-    sum = tent_row<4>(sum, ldg4(base + 1536), ldg4(base + 1536 + 4));
-    sum = tent_row<5>(sum, ldg4(base + 2048), ldg4(base + 2048 + 4));
+    sum = tent_row<1>(sum, P::load(base));
+    sum = tent_row<2>(sum, P::load(base + 2048));
+    sum = tent_row<3>(sum, P::load(base + 2 * 2048));
+    sum = tent_row<4>(sum, P::load(base + 3 * 2048));
+    sum = tent_row<5>(sum, P::load(base + 4 * 2048));
     *out = sum;
 }
 
@@ -448,6 +529,57 @@ pdqf_transform_kernel(float *__restrict__ pdqf, int op)
     base[tid] = v;
 }
 
+// one pixel to f32 luma with explicit coefficients (the trait's const generics R_COEFF/G_COEFF/B_COEFF)
+template <bool FMA>
+__device__ __forceinline__ float luma_c(float r, float g, float b, float cr, float cg, float cb)
+{
+    if (FMA)
+        return __fmaf_rn(b, cb, __fmaf_rn(g, cg, __fmul_rn(r, cr)));
+    return __fadd_rn(__fadd_rn(__fmul_rn(cr, r), __fmul_rn(cg, g)), __fmul_rn(cb, b));
+}
+
+template <int FMT, bool FMA>
+__global__ void __launch_bounds__(256)
+cvt_luma8f_kernel(const uint8_t *__restrict__ px, size_t n_pixels, float cr, float cg, float cb,
+                  float *__restrict__ out)
+{
+    constexpr int BPP = FMT == YUME_PDQ_CUDA_PIXEL_LUMA8 ? 1 : FMT == YUME_PDQ_CUDA_PIXEL_RGB8 ? 3 : 4;
+    const size_t groups = (n_pixels + 3) / 4;
+    const bool aligned = (reinterpret_cast<uintptr_t>(px) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups;
+         g += (size_t)gridDim.x * blockDim.x) {
+        const size_t p0 = 4 * g;
+        if (aligned && p0 + 4 <= n_pixels) {
+            float4 v;
+            if (FMT == YUME_PDQ_CUDA_PIXEL_LUMA8) {
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(px) + g);
+                v = make_float4(u8f(w, 0), u8f(w, 1), u8f(w, 2), u8f(w, 3));
+            } else if (FMT == YUME_PDQ_CUDA_PIXEL_RGB8) {
+                const uint32_t *q = reinterpret_cast<const uint32_t *>(px) + 3 * g;
+                const uint32_t a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+                v = make_float4(luma_c<FMA>(u8f(a, 0), u8f(a, 1), u8f(a, 2), cr, cg, cb),
+                                luma_c<FMA>(u8f(a, 3), u8f(b, 0), u8f(b, 1), cr, cg, cb),
+                                luma_c<FMA>(u8f(b, 2), u8f(b, 3), u8f(c, 0), cr, cg, cb),
+                                luma_c<FMA>(u8f(c, 1), u8f(c, 2), u8f(c, 3), cr, cg, cb));
+            } else {
+                const uint4 w = __ldg(reinterpret_cast<const uint4 *>(px) + g);
+                v = make_float4(luma_c<FMA>(u8f(w.x, 0), u8f(w.x, 1), u8f(w.x, 2), cr, cg, cb),
+                                luma_c<FMA>(u8f(w.y, 0), u8f(w.y, 1), u8f(w.y, 2), cr, cg, cb),
+                                luma_c<FMA>(u8f(w.z, 0), u8f(w.z, 1), u8f(w.z, 2), cr, cg, cb),
+                                luma_c<FMA>(u8f(w.w, 0), u8f(w.w, 1), u8f(w.w, 2), cr, cg, cb));
+            }
+            reinterpret_cast<float4 *>(out)[g] = v;
+        } else {
+            for (size_t p = p0; p < n_pixels && p < p0 + 4; p++) {
+                const uint8_t *b = px + p * BPP;
+                out[p] = FMT == YUME_PDQ_CUDA_PIXEL_LUMA8
+                             ? (float)b[0]
+                             : luma_c<FMA>((float)b[0], (float)b[1], (float)b[2], cr, cg, cb);
+            }
+        }
+    }
+}
+
 int upload_luts()
 {
     static thread_local int done_dev = -1;
@@ -467,7 +599,7 @@ int upload_luts()
 
 }  // namespace
 
-int launch_hash_batch(const float *frames, size_t n, uint8_t *hashes, float *quality,
+int launch_hash_batch(const void *frames, int pixel_format, size_t n, uint8_t *hashes, float *quality,
                       float *thresholds, float *pdqf, cudaStream_t s)
 {
     if (n == 0)
@@ -475,8 +607,52 @@ int launch_hash_batch(const float *frames, size_t n, uint8_t *hashes, float *qua
     int rc = upload_luts();
     if (rc)
         return rc;
-    unsigned grid = (unsigned)std::min<size_t>(n, (size_t)1 << 30);
-    hash_fused_kernel<<<grid, HT, 0, s>>>(frames, n, hashes, quality, thresholds, pdqf);
+    const unsigned grid = (unsigned)std::min<size_t>(n, (size_t)1 << 30);
+    const uint8_t *fr = static_cast<const uint8_t *>(frames);
+#define YPDQ_HASH_CASE(FMT, FMA)                                                                       \
+    case (FMT) | ((FMA) ? YUME_PDQ_CUDA_PIXEL_FMA : 0):                                                \
+        hash_fused_kernel<FMT, FMA><<<grid, HT, 0, s>>>(fr, n, hashes, quality, thresholds, pdqf);     \
+        break
+    switch (pixel_format) {
+        YPDQ_HASH_CASE(YUME_PDQ_CUDA_PIXEL_F32, false);
+        YPDQ_HASH_CASE(YUME_PDQ_CUDA_PIXEL_LUMA8, false);
+        YPDQ_HASH_CASE(YUME_PDQ_CUDA_PIXEL_RGB8, false);
+        YPDQ_HASH_CASE(YUME_PDQ_CUDA_PIXEL_RGB8, true);
+        YPDQ_HASH_CASE(YUME_PDQ_CUDA_PIXEL_RGBA8, false);
+        YPDQ_HASH_CASE(YUME_PDQ_CUDA_PIXEL_RGBA8, true);
+    default:
+        return YUME_PDQ_CUDA_E_INVALID;
+    }
+#undef YPDQ_HASH_CASE
+    YPDQ_LAUNCH_CHECK();
+    return 0;
+}
+
+// Kernel::cvt_rgb8_to_luma8f / cvt_rgba8_to_luma8f (mod.rs:303-340) and the LUMA8 `as f32` of main.rs:508-510
+// over n_pixels pixels (any number of rows); four pixels per thread, byte-wise tail.
+int launch_cvt_luma8f(const void *pixels, int pixel_format, size_t n_pixels, const float *coeff, float *out,
+                      cudaStream_t s)
+{
+    if (n_pixels == 0)
+        return 0;
+    const int fmt = pixel_format & ~YUME_PDQ_CUDA_PIXEL_FMA;
+    const bool fma = (pixel_format & YUME_PDQ_CUDA_PIXEL_FMA) != 0;
+    if (fmt != YUME_PDQ_CUDA_PIXEL_LUMA8 && fmt != YUME_PDQ_CUDA_PIXEL_RGB8 && fmt != YUME_PDQ_CUDA_PIXEL_RGBA8)
+        return YUME_PDQ_CUDA_E_INVALID;
+    const float cr = coeff ? coeff[0] : 0.299f, cg = coeff ? coeff[1] : 0.587f, cb = coeff ? coeff[2] : 0.114f;
+    const size_t groups = (n_pixels + 3) / 4;
+    const unsigned grid = (unsigned)std::min<size_t>((groups + 255) / 256, 148 * 16);
+    const uint8_t *px = static_cast<const uint8_t *>(pixels);
+    if (fmt == YUME_PDQ_CUDA_PIXEL_LUMA8)
+        cvt_luma8f_kernel<YUME_PDQ_CUDA_PIXEL_LUMA8, false><<<grid, 256, 0, s>>>(px, n_pixels, cr, cg, cb, out);
+    else if (fmt == YUME_PDQ_CUDA_PIXEL_RGB8 && !fma)
+        cvt_luma8f_kernel<YUME_PDQ_CUDA_PIXEL_RGB8, false><<<grid, 256, 0, s>>>(px, n_pixels, cr, cg, cb, out);
+    else if (fmt == YUME_PDQ_CUDA_PIXEL_RGB8)
+        cvt_luma8f_kernel<YUME_PDQ_CUDA_PIXEL_RGB8, true><<<grid, 256, 0, s>>>(px, n_pixels, cr, cg, cb, out);
+    else if (!fma)
+        cvt_luma8f_kernel<YUME_PDQ_CUDA_PIXEL_RGBA8, false><<<grid, 256, 0, s>>>(px, n_pixels, cr, cg, cb, out);
+    else
+        cvt_luma8f_kernel<YUME_PDQ_CUDA_PIXEL_RGBA8, true><<<grid, 256, 0, s>>>(px, n_pixels, cr, cg, cb, out);
     YPDQ_LAUNCH_CHECK();
     return 0;
 }
