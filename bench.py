@@ -375,20 +375,29 @@ def main():
             lambda: matcher.find_device(n8, 8, match_out, CAP, match_cnt), 20, flush)
         scan_bytes = shard_rows * 32
         share = m_mean / (m_mean + h_mean)
-        # Tensor roofline: one (row, needle) pair = 256 multiply-adds = 512 ops of the packed-FP4 MMA
-        # (tcgen05.mma kind::mxf4, e2m1 +-1 operands, f32 accumulate).  MEASURED_PEAKS.json holds the dense
-        # bf16 rate; the FP4 pipe is 4x the bf16 pipe (9 vs 2.25 PFLOP/s nominal), so peak = 4 x the bf16
-        # figure (the sustained one: this kernel is timed inside a long step).
+        # Tensor roofline.  At threshold <= 36 the matcher runs the 128-bit prefix filter on the tensor cores:
+        # one (row, needle) pair = 128 multiply-adds = 256 ops of the packed-FP4 MMA (tcgen05.mma kind::mxf4, e2m1
+        # +-1 operands, f32 accumulate) plus an exact POPC check of the rare candidates; above that the full
+        # 256-bit dot product, 512 ops.  `achieved` counts the tensor ops the kernel executes.  Peak: MEASURED_PEAKS.json
+        # holds a dense bf16 rate but no FP4 one, and 4 x its bf16 figure (FP4 : bf16 = 4 : 1 on the tensor pipe)
+        # is BELOW what this kernel achieves (cuBLAS bf16 on random data is power-limited to ~1.4 GHz, +-1 operands
+        # are not), so the denominator is the issue rate of the very same instruction measured live on this GPU
+        # with no loads and no epilogue (yume_pdq_cuda_measure_mxf4_peak); the bf16-derived figure is kept beside it.
+        ops_per_pair = 256 if THRESHOLD <= 36 else 512
         bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
-        tensor_peak = 4.0 * bf16
-        achieved_tops = pairs * 512 / (m_mean * 1e-3) / 1e12
+        mxf4_peak, mxf4_clk = yp.measure_mxf4_peak(local_rank, 20000)
+        achieved_tops = pairs * ops_per_pair / (m_mean * 1e-3) / 1e12
         line_extra["roofline"] = {
-            "kernel": "match_tensor4_kernel (tcgen05.mma kind::mxf4; needle batch %d x this rank's %d-row shard)"
-                      % (B * 8, shard_rows),
-            "bound": "tensor", "achieved": achieved_tops, "peak": tensor_peak, "unit": "TFLOP/s",
-            "frac": achieved_tops / tensor_peak,
-            "peak_source": ("4 x bf16_tflops_sustained of MEASURED_PEAKS.json (FP4 : bf16 = 4 : 1 on the tensor "
-                            "pipe); raw mxf4 issue rate measured on this pool by tools/mma_peak.cu: 8900 TFLOP/s"),
+            "kernel": "match_tensor4_kernel<%s> (tcgen05.mma kind::mxf4; needle batch %d x this rank's %d-row shard)"
+                      % ("128-bit prefix filter" if ops_per_pair == 256 else "256-bit", B * 8, shard_rows),
+            "bound": "tensor", "achieved": achieved_tops, "peak": mxf4_peak, "unit": "TFLOP/s",
+            "frac": achieved_tops / mxf4_peak,
+            "peak_source": ("live: back-to-back tcgen05.mma kind::mxf4 M128 N240 K64 on this GPU, %.1f SM clk per MMA "
+                            "(yume_pdq_cuda_measure_mxf4_peak)" % mxf4_clk),
+            "peak_bf16_x4": 4.0 * bf16, "frac_of_bf16_x4": achieved_tops / (4.0 * bf16),
+            "peak_bf16_x4_source": "4 x bf16_tflops_sustained of MEASURED_PEAKS.json" if peaks else
+                                   "4 x 1590 (B200_PROFILING.md fallback)",
+            "tensor_ops_per_pair": ops_per_pair,
             "tpairs_per_s": pairs / (m_mean * 1e-3) / 1e12,
             "traffic": None, "ms_per_launch": m_mean, "share_of_step": share,
         }
@@ -438,7 +447,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         e2e = {"value": n_gpus * B * e2e_steps / dt, "unit": UNIT,
-               "h2d_bytes_per_step": int(B * 512 * 512 * 4 + B * 8 * 32),
+               "h2d_bytes_per_step": int(B * 512 * 512 * 4),
                "d2h_bytes_per_step": int(B * 8 * 32 + 16 + len(m) * 16) if n_gpus == 1 else
                int(B * 8 * 32 + 4 + (1 << 16) * 16 * n_gpus),
                "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
@@ -447,6 +456,43 @@ def main():
                         "ShardedMatcher.screen(pinned host frames): chunked H2D || yume_pdq_cuda_hash_batch -> NCCL "
                         "all-gather -> yume_pdq_cuda_matcher_find_device_base, then gather + merge of match lists")}
         del host_frames
+
+        # the same call with 8-bit luma frames (what the reference's `pipe` ingests, main.rs:486-510): the input
+        # conversion is fused into the hash kernel, so a frame crosses PCIe as 256 KiB instead of 1 MiB
+        dev8 = torch.empty((B, 512, 512), dtype=torch.uint8, device=dev)
+        yp.synth_pixels(dev8, B, yp.PIXEL_LUMA8, first_frame=rank * B, seed=SEED, device=local_rank)
+        want8 = kern.hash_batch(dev8, want_quality=False, want_thresholds=False, pixel_format=yp.PIXEL_LUMA8)["hashes"]
+        host8 = torch.empty((B, 512, 512), dtype=torch.uint8, pin_memory=True)
+        host8.copy_(dev8)
+        del dev8
+
+        def e2e8_step():
+            if n_gpus == 1:
+                return matcher.screen(host8.numpy(), hashes=host_hashes, pixel_format=yp.PIXEL_LUMA8)
+            m8 = sm.screen(host8, hashes_out=outs["hashes"], pixel_format=yp.PIXEL_LUMA8)
+            host_hashes_t.copy_(outs["hashes"])
+            return m8
+
+        e2e8_step()
+        if not np.array_equal(host_hashes, want8.cpu().numpy()):
+            raise SystemExit("bench.py: LUMA8 end-to-end hashes differ from the device-resident path")
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            m8 = e2e8_step()
+        barrier()
+        dt8 = time.perf_counter() - t0
+        tt = torch.tensor([dt8], dtype=torch.float64, device=dev)
+        if n_gpus > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt8 = float(tt.item())
+        e2e["luma8"] = {"value": n_gpus * B * e2e_steps / dt8, "unit": UNIT,
+                        "h2d_bytes_per_step": int(B * 512 * 512), "ms_per_step": dt8 / e2e_steps * 1e3,
+                        "d2h_bytes_per_step": int(B * 8 * 32 + 16 + len(m8) * 16) if n_gpus == 1 else
+                        int(B * 8 * 32 + 4 + (1 << 16) * 16 * n_gpus),
+                        "path": "the same call with pinned 8-bit luma frames (yume_pdq_cuda_screen_batch_pixels, "
+                                "YUME_PDQ_CUDA_PIXEL_LUMA8): conversion fused into the hash kernel"}
+        del host8
 
     cpu_bl = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:

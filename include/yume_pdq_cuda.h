@@ -204,8 +204,10 @@ int yume_pdq_cuda_db_write_rows(YumePDQ_CudaDb *db, size_t first_local_row, cons
 #define YUME_PDQ_CUDA_ALGO_EXACT 1   /* unfiltered: 8 POPC per (row, needle) pair */
 #define YUME_PDQ_CUDA_ALGO_TILED 2   /* rows in registers x needles in smem, 96-bit carry-save prefilter */
 #define YUME_PDQ_CUDA_ALGO_STREAM 3  /* TMA bulk-copy ring + prefilter, needle prefixes in registers (q <= 32) */
-#define YUME_PDQ_CUDA_ALGO_TENSOR 4  /* tcgen05.mma kind::mxf4 on +-1.0 e2m1 expanded bits (thresholds > 127: kind::i8): large needle batches */
+#define YUME_PDQ_CUDA_ALGO_TENSOR 4  /* tcgen05.mma kind::mxf4 on +-1.0 e2m1 expanded bits: large needle batches. thresholds <= 36: 128-bit prefix filter on the tensor cores + exact POPC check of the candidates; <= 127: full 256-bit dot products; > 127: kind::i8 */
 #define YUME_PDQ_CUDA_ALGO_TENSOR_I8 5  /* tcgen05.mma kind::i8 on +-1 int8 expanded bits, any threshold */
+#define YUME_PDQ_CUDA_ALGO_TENSOR_FULL 6    /* kind::mxf4, always the full 256-bit dot product (threshold <= 127) */
+#define YUME_PDQ_CUDA_ALGO_TENSOR_PREFIX 7  /* kind::mxf4, always the 128-bit prefix filter (threshold <= 63) */
 
 /* PDQMatcher::scan (matching/mod.rs:72-79): *matched = 1 iff any needle is within
  * `threshold` (inclusive) of any row.  needles q x 32 bytes, host or device. */
@@ -255,6 +257,13 @@ int yume_pdq_cuda_screen_batch(YumePDQ_CudaDb *db, const float *frames, size_t n
 int yume_pdq_cuda_screen_batch_pixels(YumePDQ_CudaDb *db, const void *frames, int pixel_format, size_t n,
                                       uint32_t threshold, uint8_t *hashes, float *quality,
                                       YumePDQ_Match *out, size_t cap, size_t *n_found, void *stream);
+
+/* ---- measurement helper ----
+ * Raw issue rate of the instruction the tensor matcher is built on (tcgen05.mma kind::mxf4.block_scale,
+ * M 128, N 240, K 64, +-1.0 e2m1 operands, f32 accumulate) with no loads and no epilogue: one CTA per
+ * SM issues `iters` x 8 MMAs back to back.  *tera_ops = 2 * M * N * K * MMAs / time / 1e12 (the roofline
+ * denominator bench.py reports for that kernel); *sm_clk_per_mma (nullable) from clock64(). */
+int yume_pdq_cuda_measure_mxf4_peak(int device, int iters, double *tera_ops, double *sm_clk_per_mma);
 
 /* ---- synthetic inputs (device-side generators shared with the oracle) ----
  * frames_dev n x 512 x 512 f32 DEVICE pointer. kind 0: uniform 8-bit noise;

@@ -38,7 +38,8 @@ def test_planted_vs_oracle_all_algos(cuda, oracle, n_rows, q):
     assert match_tuples(m.find_all(needles)) == want          # sorted (row, needle) like CpuMatcher::find
     assert m.scan(needles) == (len(want) > 0)
     assert m.find_min(needles) == oracle.matcher_find_min(rows, needles, 31)
-    for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_STREAM, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8):
+    for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_STREAM, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8,
+                 cuda.ALGO_TENSOR_FULL, cuda.ALGO_TENSOR_PREFIX):
         assert _find_device(cuda, m, needles, algo) == sorted(want), algo
     db.close()
 
@@ -61,10 +62,23 @@ def test_thresholds(cuda, oracle, threshold):
     if threshold <= 40:
         for algo in (cuda.ALGO_TILED, cuda.ALGO_STREAM):
             assert _find_device(cuda, m, needles, algo, cap=1 << 18) == sorted(want)
-    if len(want) < 200_000:     # the tensor-core path has no prefilter: exact for every threshold
+    if len(want) < 200_000:     # the tensor-core paths are exact for every threshold they accept
         assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR, cap=1 << 18) == sorted(want)
         assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_I8, cap=1 << 18) == sorted(want)
+        if threshold <= 127:
+            assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_FULL, cap=1 << 18) == sorted(want)
+        if threshold <= 63:    # beyond 36 nearly every pair is a candidate: slow, still exact
+            assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_PREFIX, cap=1 << 18) == sorted(want)
     db.close()
+    # the forced variants reject thresholds they cannot represent instead of answering wrongly
+    if threshold > 127:
+        with pytest.raises(cuda.YumePdqCudaError):
+            _find_device(cuda, cuda.CudaMatcher(cuda.CudaVectorDatabase(rows[:64]), threshold), needles,
+                         cuda.ALGO_TENSOR_FULL)
+    if threshold > 63:
+        with pytest.raises(cuda.YumePdqCudaError):
+            _find_device(cuda, cuda.CudaMatcher(cuda.CudaVectorDatabase(rows[:64]), threshold), needles,
+                         cuda.ALGO_TENSOR_PREFIX)
 
 
 def test_reference_planted_positive_procedure(cuda, oracle):
@@ -106,6 +120,50 @@ def test_large_needle_batch_multi_chunk(cuda, oracle):
     assert _find_device(cuda, m, needles, cuda.ALGO_TILED) == sorted(want)
     assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR) == sorted(want)
     assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_I8) == sorted(want)
+    assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_FULL) == sorted(want)
+    assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_PREFIX) == sorted(want)
+    db.close()
+
+
+def _flip_in(h, k_lo, k_hi, rng):
+    """Copy of hash h with exactly k_lo distinct bits flipped inside bytes 0..15 (the 128 bits the tensor prefix
+    filter looks at) and k_hi inside bytes 16..31."""
+    bits = np.unpackbits(h)
+    pos = np.concatenate([rng.choice(128, size=k_lo, replace=False), 128 + rng.choice(128, size=k_hi, replace=False)])
+    bits[pos.astype(np.int64)] ^= 1
+    return np.packbits(bits)
+
+
+@pytest.mark.parametrize("q", [8, 700])
+def test_prefix_filter_boundaries(cuda, oracle, q):
+    """The 128-bit prefix filter of the tensor matcher: a pair is a candidate iff its distance over bytes 0..15 is
+    <= threshold, and a candidate is a match iff its full distance is.  Plants pin both decisions on both sides."""
+    rng = np.random.default_rng(1000 + q)
+    rows = oracle.synth_db(50_021, first_row=5)
+    needles = rng.integers(0, 256, size=(q, 32), dtype=np.uint8)
+    cases = [(31, 0), (0, 31), (16, 15), (32, 0), (0, 32), (31, 1), (30, 1), (20, 20), (1, 31), (0, 0), (31, 97),
+             (64, 0), (0, 128)]
+    pos = rng.choice(rows.shape[0], size=len(cases) * 8, replace=False)
+    k = 0
+    for rep in range(8):
+        for lo, hi in cases:
+            rows[pos[k]] = _flip_in(needles[(rep * 89 + 7 * k) % q], lo, hi, rng)
+            k += 1
+    # tile edges: last row of a 240-row tile / 480-row super-tile, first of the next, last row of the DB
+    for r in (239, 240, 479, 480, rows.shape[0] - 1):
+        rows[r] = _flip_in(needles[r % q], 15, 16, rng)
+    want = sorted(match_tuples(oracle.matcher_find(rows, needles, 31)))
+    assert len(want) >= 8 * 5 + 5
+    db = cuda.CudaVectorDatabase(rows)
+    m = cuda.CudaMatcher(db, 31)
+    for algo in (cuda.ALGO_TENSOR_PREFIX, cuda.ALGO_TENSOR_FULL, cuda.ALGO_TENSOR, cuda.ALGO_AUTO):
+        assert _find_device(cuda, m, needles, algo) == want, algo
+    for thr in (0, 15, 36, 37, 50, 63):
+        mt = cuda.CudaMatcher(db, thr)
+        w = sorted(match_tuples(oracle.matcher_find(rows, needles, thr)))
+        if q <= 8 or thr <= 37:        # 700 needles at thr 50+: every pair is a candidate, slow but covered at q = 8
+            assert _find_device(cuda, mt, needles, cuda.ALGO_TENSOR_PREFIX, cap=1 << 18) == w, thr
+        assert _find_device(cuda, mt, needles, cuda.ALGO_TENSOR, cap=1 << 18) == w, thr
     db.close()
 
 
@@ -123,7 +181,8 @@ def test_adversarial_dense_matches(cuda, oracle):
     m = cuda.CudaMatcher(db, 31)
     got = m.find_all(needles, cap=1000)        # forces the E_CAPACITY retry path
     assert match_tuples(got) == want
-    for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8):
+    for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8, cuda.ALGO_TENSOR_FULL,
+                 cuda.ALGO_TENSOR_PREFIX):
         assert _find_device(cuda, m, needles, algo, cap=1 << 19) == sorted(want)
     assert _find_device(cuda, m, needles[:32], cuda.ALGO_STREAM, cap=1 << 19) == sorted(
         t for t in want if t[1] < 32)
@@ -187,7 +246,8 @@ def test_headline_config_10m(cuda, oracle):
     want = sorted(p for p in planted if p[2] <= 31)
     assert match_tuples(m.find_all(needles)) == want
     assert m.find_min(needles) == (want[0][0], want[0][1])
-    for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_STREAM, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8):
+    for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_STREAM, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8,
+                 cuda.ALGO_TENSOR_FULL, cuda.ALGO_TENSOR_PREFIX):
         assert _find_device(cuda, m, needles, algo) == want
     # last rows of the last chunk are planted too (tail handling)
     db.write_rows(n - 1, needles[5][None])

@@ -76,6 +76,44 @@ def main():
                   f"{n * q / med / 1e6:8.3f} Tpairs/s  hits={int(cnt.item())}")
             cnt.zero_()
         db.close()
+    if "tc4p" in what:   # full 256-bit vs 128-bit prefix tensor matcher (run once per YUME_PDQ_CUDA_LIB variant)
+        tag = os.path.basename(os.environ.get("YUME_PDQ_CUDA_LIB", "default"))
+        peak, clk = yp.measure_mxf4_peak(0)
+        print(f"[{tag}] mxf4 issue rate: {peak:.0f} Tops/s, {clk:.1f} SM clk per MMA (M128 N240 K64)")
+        n = (10_000_000 // 2048 + 1) * 2048
+        db = yp.CudaVectorDatabase(synthetic_rows=n)
+        m = yp.CudaMatcher(db, 31)
+        out = torch.zeros((1 << 20, 16), dtype=torch.uint8, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for q in (1024, 4096, 32768):
+            needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
+            for name, algo in (("full", yp.ALGO_TENSOR_FULL), ("prefix", yp.ALGO_TENSOR_PREFIX)):
+                med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 20, cnt, algo=algo), iters=5, warm=1)
+                print(f"[{tag}] match 10M x {q:6d} {name:6s}: median {med / 1e3:9.2f} ms  {n * q / med / 1e6:8.3f} Tpairs/s  "
+                      f"hits={int(cnt.item())}")
+                cnt.zero_()
+        for thr in (36, 40):   # candidate-rate sensitivity of the prefix filter
+            mt = yp.CudaMatcher(db, thr)
+            needles = torch.from_numpy(rng.integers(0, 256, size=(32768, 32), dtype=np.uint8)).cuda()
+            med, best = timeit(lambda: mt.find_device(needles, 32768, out, 1 << 20, cnt, algo=yp.ALGO_TENSOR_PREFIX),
+                               iters=3, warm=1)
+            print(f"[{tag}] match 10M x  32768 prefix thr={thr}: median {med / 1e3:9.2f} ms  {n * 32768 / med / 1e6:8.3f} Tpairs/s")
+            cnt.zero_()
+        db.close()
+    if "hashpx" in what:   # hash kernel per pixel format
+        k = yp.CudaKernel(0)
+        n = 4096
+        outs = {"hashes": torch.empty((n, 8, 32), dtype=torch.uint8, device="cuda"),
+                "quality": torch.empty((n, 8), dtype=torch.float32, device="cuda"),
+                "thresholds": torch.empty((n, 8), dtype=torch.float32, device="cuda")}
+        for name, fmt, ch in (("LUMA8", yp.PIXEL_LUMA8, 1), ("RGB8", yp.PIXEL_RGB8, 3), ("RGBA8", yp.PIXEL_RGBA8, 4),
+                              ("RGBA8+FMA", yp.PIXEL_RGBA8 | yp.PIXEL_FMA, 4)):
+            frames = torch.empty((n, 512, 512) if ch == 1 else (n, 512, 512, ch), dtype=torch.uint8, device="cuda")
+            yp.synth_pixels(frames, n, fmt)
+            med, best = timeit(lambda: k.hash_batch(frames, out=outs, pixel_format=fmt), iters=10, flush=flush)
+            print(f"hash {n} {name:9s} frames: median {med:9.1f} us  best {best:9.1f} us  {n / med:7.3f} Mimg/s  "
+                  f"{n * 262144 * ch / med / 1e3:7.1f} GB/s")
+            del frames
     if "tc4clk" in what:   # SM clock / power while the tensor matcher runs back to back for ~1.5 s
         import subprocess, tempfile
         n = (10_000_000 // 2048 + 1) * 2048

@@ -23,11 +23,13 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libyume_pdq_cuda.so")
+# YUME_PDQ_CUDA_LIB: developer knob, an experimental build of the same library (yume_pdq_b200/build.py variant)
+LIB_PATH = os.environ.get("YUME_PDQ_CUDA_LIB") or os.path.join(HERE, "libyume_pdq_cuda.so")
 
 MATCH_DTYPE = np.dtype([("row", "<u8"), ("needle", "<u4"), ("dist", "<u4")])
 
 ALGO_AUTO, ALGO_EXACT, ALGO_TILED, ALGO_STREAM, ALGO_TENSOR, ALGO_TENSOR_I8 = 0, 1, 2, 3, 4, 5
+ALGO_TENSOR_FULL, ALGO_TENSOR_PREFIX = 6, 7
 
 OP_T = 0
 OP_NEGATE_ALT_COLS_FALSE = 1
@@ -107,6 +109,7 @@ SIGNATURES = {
                                              C.POINTER(C.c_size_t), _vp]),
     "yume_pdq_cuda_screen_batch_pixels": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t, C.c_uint32, _vp, _vp, _vp,
                                                     C.c_size_t, C.POINTER(C.c_size_t), _vp]),
+    "yume_pdq_cuda_measure_mxf4_peak": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "yume_pdq_cuda_synth_pixels": (C.c_int, [C.c_int, _vp, C.c_int, C.c_size_t, C.c_uint64, C.c_uint64, _vp]),
     "yume_pdq_cuda_synth_frames": (C.c_int, [C.c_int, _vp, C.c_size_t, C.c_uint64, C.c_uint64, C.c_int, _vp]),
     "yume_pdq_cuda_synth_rows": (C.c_int, [C.c_int, _vp, C.c_size_t, C.c_uint64, C.c_uint64, _vp]),
@@ -551,6 +554,14 @@ def synth_frames(frames_dev, n: int, first_frame: int = 0, seed: int = 0x79756D6
                  device: int = 0, stream=None):
     _check(lib.yume_pdq_cuda_synth_frames(device, _ptr(frames_dev), n, first_frame, seed, kind,
                                           _stream(stream)), "synth_frames")
+
+
+def measure_mxf4_peak(device: int = 0, iters: int = 20000):
+    """(tera-ops/s, SM clocks per MMA) of back-to-back tcgen05.mma kind::mxf4 M128 N240 K64: the live roofline
+    denominator of the tensor matcher."""
+    t, c = C.c_double(0), C.c_double(0)
+    _check(lib.yume_pdq_cuda_measure_mxf4_peak(device, iters, C.byref(t), C.byref(c)), "measure_mxf4_peak")
+    return float(t.value), float(c.value)
 
 
 def synth_pixels(frames_dev, n: int, pixel_format: int, first_frame: int = 0, seed: int = 0x79756D652D706471,

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libyume_pdq_cuda.so")
-SOURCES = ["api.cu", "hasher.cu", "matcher.cu", "matcher_tc.cu", "matcher_tc4.cu", "synth.cu"]
+SOURCES = ["api.cu", "hasher.cu", "matcher.cu", "matcher_tc.cu", "matcher_tc4.cu", "synth.cu", "peak.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--shared",
@@ -32,6 +32,18 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(tag: str, defines: list[str]) -> str:
+    """Developer builds for kernel experiments (tools/quick_bench.py, YUME_PDQ_CUDA_LIB): the same sources with
+    extra -D flags into libyume_pdq_cuda_<tag>.so.  Not used by the product or the tests."""
+    out = os.path.join(HERE, f"libyume_pdq_cuda_{tag}.so")
+    cmd = [_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
@@ -49,4 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    build(force=True, verbose=True)
+    if len(sys.argv) > 2 and sys.argv[1] == "variant":      # python -m yume_pdq_b200.build variant <tag> <DEFINE>...
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+    else:
+        build(force=True, verbose=True)

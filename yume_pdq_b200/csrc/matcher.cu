@@ -440,7 +440,10 @@ int launch_match(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const 
         algo = YUME_PDQ_CUDA_ALGO_TILED;
     if (algo == YUME_PDQ_CUDA_ALGO_TENSOR && threshold <= 127)
         return launch_match_tensor4(rows, n_rows, row_offset, needles, q, threshold, out, cap, count, min_key,
-                                    mode, sm_count, s, needle_base);
+                                    mode, sm_count, s, needle_base, -1);
+    if (algo == YUME_PDQ_CUDA_ALGO_TENSOR_FULL || algo == YUME_PDQ_CUDA_ALGO_TENSOR_PREFIX)
+        return launch_match_tensor4(rows, n_rows, row_offset, needles, q, threshold, out, cap, count, min_key,
+                                    mode, sm_count, s, needle_base, algo == YUME_PDQ_CUDA_ALGO_TENSOR_PREFIX);
     if (algo == YUME_PDQ_CUDA_ALGO_TENSOR || algo == YUME_PDQ_CUDA_ALGO_TENSOR_I8)
         return launch_match_tensor(rows, n_rows, row_offset, needles, q, threshold, out, cap, count, min_key,
                                    mode, sm_count, s, needle_base);

@@ -116,11 +116,13 @@ class ShardedMatcher:
         import torch
         return gather_match_lists(local, cap, device=torch.device("cuda", self.device), group=self.group)
 
-    def screen(self, local_frames, hashes_out=None, cap: int = 1 << 16, chunk: int = 128) -> np.ndarray:
+    def screen(self, local_frames, hashes_out=None, cap: int = 1 << 16, chunk: int = 128,
+               pixel_format: int = 0) -> np.ndarray:
         """Pipelined multi-GPU hash + match (BASELINE config 4: video screening against a sharded DB).
 
-        ``local_frames``: this rank's [n_local, 512, 512] f32 frames -- a (pinned) host numpy array /
-        CPU tensor, or a CUDA tensor; every rank passes the same n_local.  Per chunk of ``chunk`` frames:
+        ``local_frames``: this rank's [n_local, 512, 512] f32 frames (or 8-bit frames in ``pixel_format``:
+        u8 [n, 512, 512], [n, 512, 512, 3] or [n, 512, 512, 4]) -- a (pinned) host numpy array / CPU tensor,
+        or a CUDA tensor; every rank passes the same n_local.  Per chunk of ``chunk`` frames:
         [H2D of chunk i+1 on a copy stream] || [hash chunk i -> all-gather its 8 * chunk needles over
         NCCL -> match the world * 8 * chunk gathered needles against this rank's row shard].  One host
         synchronisation at the end, then the gather + merge of the match lists.  Returns, on every rank,
@@ -131,13 +133,13 @@ class ShardedMatcher:
         import torch.distributed as dist
         from . import CudaKernel, MATCH_DTYPE as MD
         if self.world == 1:
-            return self.matcher.screen(local_frames, hashes=hashes_out, cap=cap)
+            return self.matcher.screen(local_frames, hashes=hashes_out, cap=cap, pixel_format=pixel_format)
         dev = torch.device("cuda", self.device)
         n = int(local_frames.shape[0])
         W = self.world
         on_host = not (hasattr(local_frames, "is_cuda") and local_frames.is_cuda)
         if on_host and not hasattr(local_frames, "is_cuda"):
-            local_frames = torch.from_numpy(np.ascontiguousarray(local_frames, dtype=np.float32))
+            local_frames = torch.from_numpy(np.ascontiguousarray(local_frames))
         kern = CudaKernel(self.device)
         hashes = hashes_out if hashes_out is not None else torch.empty((n, 8, 32), dtype=torch.uint8, device=dev)
         gath = [torch.empty((W * chunk * 8, 32), dtype=torch.uint8, device=dev) for _ in range(2)]
@@ -146,7 +148,8 @@ class ShardedMatcher:
         main = torch.cuda.current_stream(dev)
         if on_host:
             copy = torch.cuda.Stream(dev)
-            bufs = [torch.empty((chunk, 512, 512), dtype=torch.float32, device=dev) for _ in range(2)]
+            bufs = [torch.empty((chunk,) + tuple(local_frames.shape[1:]), dtype=local_frames.dtype, device=dev)
+                    for _ in range(2)]
             ev_copied = [torch.cuda.Event() for _ in range(2)]
             ev_done = [torch.cuda.Event() for _ in range(2)]
         n_chunks = (n + chunk - 1) // chunk
@@ -163,7 +166,8 @@ class ShardedMatcher:
                 src = bufs[b][:k]
             else:
                 src = local_frames[f0:f0 + k]
-            kern.hash_batch(src, want_quality=False, want_thresholds=False, out={"hashes": hashes[f0:f0 + k]})
+            kern.hash_batch(src, want_quality=False, want_thresholds=False, out={"hashes": hashes[f0:f0 + k]},
+                            pixel_format=pixel_format)
             if on_host:
                 ev_done[b].record(main)
             g = gath[b][: W * k * 8]
@@ -176,7 +180,7 @@ class ShardedMatcher:
         dist.all_reduce(worst, op=dist.ReduceOp.MAX, group=self.group)
         total, worst = int(cnt.item()), int(worst.item())
         if worst > cap:
-            return self.screen(local_frames, hashes_out=hashes_out, cap=worst, chunk=chunk)
+            return self.screen(local_frames, hashes_out=hashes_out, cap=worst, chunk=chunk, pixel_format=pixel_format)
         local = out[:total].cpu().numpy().view(MD).reshape(-1).copy()
         cidx = local["needle"] // (W * chunk * 8)
         p = local["needle"] % (W * chunk * 8)
