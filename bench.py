@@ -375,21 +375,27 @@ def main():
             lambda: matcher.find_device(n8, 8, match_out, CAP, match_cnt), 20, flush)
         scan_bytes = shard_rows * 32
         share = m_mean / (m_mean + h_mean)
-        # Tensor roofline.  At threshold <= 36 the matcher runs the 128-bit prefix filter on the tensor cores:
-        # one (row, needle) pair = 128 multiply-adds = 256 ops of the packed-FP4 MMA (tcgen05.mma kind::mxf4, e2m1
-        # +-1 operands, f32 accumulate) plus an exact POPC check of the rare candidates; above that the full
-        # 256-bit dot product, 512 ops.  `achieved` counts the tensor ops the kernel executes.  Peak: MEASURED_PEAKS.json
-        # holds a dense bf16 rate but no FP4 one, and 4 x its bf16 figure (FP4 : bf16 = 4 : 1 on the tensor pipe)
-        # is BELOW what this kernel achieves (cuBLAS bf16 on random data is power-limited to ~1.4 GHz, +-1 operands
-        # are not), so the denominator is the issue rate of the very same instruction measured live on this GPU
-        # with no loads and no epilogue (yume_pdq_cuda_measure_mxf4_peak); the bf16-derived figure is kept beside it.
-        ops_per_pair = 256 if THRESHOLD <= 36 else 512
+        # Tensor roofline.  At threshold <= 36 the matcher runs the 128-bit prefix filter on the tensor cores with two
+        # rows per accumulator column (match_tensor4x2_kernel): ALGORITHMIC work of one (row, needle) pair = 128
+        # multiply-adds = 256 ops of the packed-FP4 MMA (tcgen05.mma kind::mxf4, e2m1 +-1 operands, f32 accumulate)
+        # plus an exact POPC check of the rare candidates; the kernel EXECUTES 320 ops per pair (a fifth MMA per
+        # tile adds the constant that aligns the two s16 fields of the accumulator).  Above threshold 36 the full
+        # 256-bit dot product runs (match_tensor4_kernel), 512 ops.  `achieved` counts the algorithmic ops,
+        # `executed_frac` the ops the tensor pipe actually performs.  Peak: MEASURED_PEAKS.json holds a dense bf16
+        # rate but no FP4 one, and 4 x its bf16 figure (FP4 : bf16 = 4 : 1 on the tensor pipe) is BELOW what this
+        # kernel achieves (cuBLAS bf16 on random data is power-limited to ~1.4 GHz, +-1 operands are not), so the
+        # denominator is the issue rate of the very same instruction measured live on this GPU with no loads and no
+        # epilogue (yume_pdq_cuda_measure_mxf4_peak); the bf16-derived figure is kept beside it.
+        paired = THRESHOLD <= 36
+        ops_per_pair = 256 if paired else 512
+        executed_per_pair = 320 if paired else 512
         bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
         mxf4_peak, mxf4_clk = yp.measure_mxf4_peak(local_rank, 20000)
         achieved_tops = pairs * ops_per_pair / (m_mean * 1e-3) / 1e12
         line_extra["roofline"] = {
-            "kernel": "match_tensor4_kernel<%s> (tcgen05.mma kind::mxf4; needle batch %d x this rank's %d-row shard)"
-                      % ("128-bit prefix filter" if ops_per_pair == 256 else "256-bit", B * 8, shard_rows),
+            "kernel": "%s (tcgen05.mma kind::mxf4; needle batch %d x this rank's %d-row shard)"
+                      % ("match_tensor4x2_kernel: 128-bit prefix filter, two rows per f32 accumulator" if paired else
+                         "match_tensor4_kernel<256-bit>", B * 8, shard_rows),
             "bound": "tensor", "achieved": achieved_tops, "peak": mxf4_peak, "unit": "TFLOP/s",
             "frac": achieved_tops / mxf4_peak,
             "peak_source": ("live: back-to-back tcgen05.mma kind::mxf4 M128 N240 K64 on this GPU, %.1f SM clk per MMA "
@@ -397,7 +403,8 @@ def main():
             "peak_bf16_x4": 4.0 * bf16, "frac_of_bf16_x4": achieved_tops / (4.0 * bf16),
             "peak_bf16_x4_source": "4 x bf16_tflops_sustained of MEASURED_PEAKS.json" if peaks else
                                    "4 x 1590 (B200_PROFILING.md fallback)",
-            "tensor_ops_per_pair": ops_per_pair,
+            "tensor_ops_per_pair": ops_per_pair, "executed_tensor_ops_per_pair": executed_per_pair,
+            "executed_frac": pairs * executed_per_pair / (m_mean * 1e-3) / 1e12 / mxf4_peak,
             "tpairs_per_s": pairs / (m_mean * 1e-3) / 1e12,
             "traffic": None, "ms_per_launch": m_mean, "share_of_step": share,
         }

@@ -204,10 +204,11 @@ int yume_pdq_cuda_db_write_rows(YumePDQ_CudaDb *db, size_t first_local_row, cons
 #define YUME_PDQ_CUDA_ALGO_EXACT 1   /* unfiltered: 8 POPC per (row, needle) pair */
 #define YUME_PDQ_CUDA_ALGO_TILED 2   /* rows in registers x needles in smem, 96-bit carry-save prefilter */
 #define YUME_PDQ_CUDA_ALGO_STREAM 3  /* TMA bulk-copy ring + prefilter, needle prefixes in registers (q <= 32) */
-#define YUME_PDQ_CUDA_ALGO_TENSOR 4  /* tcgen05.mma kind::mxf4 on +-1.0 e2m1 expanded bits: large needle batches. thresholds <= 36: 128-bit prefix filter on the tensor cores + exact POPC check of the candidates; <= 127: full 256-bit dot products; > 127: kind::i8 */
+#define YUME_PDQ_CUDA_ALGO_TENSOR 4  /* tcgen05.mma kind::mxf4 on +-1.0 e2m1 expanded bits: large needle batches. thresholds <= 36: 128-bit prefix filter on the tensor cores, two rows per accumulator (ALGO_TENSOR_PAIRED) + exact POPC check of the candidates; <= 127: full 256-bit dot products; > 127: kind::i8 */
 #define YUME_PDQ_CUDA_ALGO_TENSOR_I8 5  /* tcgen05.mma kind::i8 on +-1 int8 expanded bits, any threshold */
 #define YUME_PDQ_CUDA_ALGO_TENSOR_FULL 6    /* kind::mxf4, always the full 256-bit dot product (threshold <= 127) */
 #define YUME_PDQ_CUDA_ALGO_TENSOR_PREFIX 7  /* kind::mxf4, always the 128-bit prefix filter (threshold <= 63) */
+#define YUME_PDQ_CUDA_ALGO_TENSOR_PAIRED 8  /* kind::mxf4, 128-bit prefix filter with two rows per f32 accumulator (s16x2 fields; threshold <= 63) */
 
 /* PDQMatcher::scan (matching/mod.rs:72-79): *matched = 1 iff any needle is within
  * `threshold` (inclusive) of any row.  needles q x 32 bytes, host or device. */

@@ -39,7 +39,7 @@ def test_planted_vs_oracle_all_algos(cuda, oracle, n_rows, q):
     assert m.scan(needles) == (len(want) > 0)
     assert m.find_min(needles) == oracle.matcher_find_min(rows, needles, 31)
     for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_STREAM, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8,
-                 cuda.ALGO_TENSOR_FULL, cuda.ALGO_TENSOR_PREFIX):
+                 cuda.ALGO_TENSOR_FULL, cuda.ALGO_TENSOR_PREFIX, cuda.ALGO_TENSOR_PAIRED):
         assert _find_device(cuda, m, needles, algo) == sorted(want), algo
     db.close()
 
@@ -69,6 +69,7 @@ def test_thresholds(cuda, oracle, threshold):
             assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_FULL, cap=1 << 18) == sorted(want)
         if threshold <= 63:    # beyond 36 nearly every pair is a candidate: slow, still exact
             assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_PREFIX, cap=1 << 18) == sorted(want)
+            assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_PAIRED, cap=1 << 18) == sorted(want)
     db.close()
     # the forced variants reject thresholds they cannot represent instead of answering wrongly
     if threshold > 127:
@@ -79,6 +80,9 @@ def test_thresholds(cuda, oracle, threshold):
         with pytest.raises(cuda.YumePdqCudaError):
             _find_device(cuda, cuda.CudaMatcher(cuda.CudaVectorDatabase(rows[:64]), threshold), needles,
                          cuda.ALGO_TENSOR_PREFIX)
+        with pytest.raises(cuda.YumePdqCudaError):
+            _find_device(cuda, cuda.CudaMatcher(cuda.CudaVectorDatabase(rows[:64]), threshold), needles,
+                         cuda.ALGO_TENSOR_PAIRED)
 
 
 def test_reference_planted_positive_procedure(cuda, oracle):
@@ -122,6 +126,7 @@ def test_large_needle_batch_multi_chunk(cuda, oracle):
     assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_I8) == sorted(want)
     assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_FULL) == sorted(want)
     assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_PREFIX) == sorted(want)
+    assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_PAIRED) == sorted(want)
     db.close()
 
 
@@ -150,21 +155,52 @@ def test_prefix_filter_boundaries(cuda, oracle, q):
             rows[pos[k]] = _flip_in(needles[(rep * 89 + 7 * k) % q], lo, hi, rng)
             k += 1
     # tile edges: last row of a 240-row tile / 480-row super-tile, first of the next, last row of the DB
-    for r in (239, 240, 479, 480, rows.shape[0] - 1):
+    for r in (239, 240, 479, 480, 719, 720, 959, 960, 1199, 1200, rows.shape[0] - 1):
         rows[r] = _flip_in(needles[r % q], 15, 16, rng)
     want = sorted(match_tuples(oracle.matcher_find(rows, needles, 31)))
     assert len(want) >= 8 * 5 + 5
     db = cuda.CudaVectorDatabase(rows)
     m = cuda.CudaMatcher(db, 31)
-    for algo in (cuda.ALGO_TENSOR_PREFIX, cuda.ALGO_TENSOR_FULL, cuda.ALGO_TENSOR, cuda.ALGO_AUTO):
+    for algo in (cuda.ALGO_TENSOR_PREFIX, cuda.ALGO_TENSOR_PAIRED, cuda.ALGO_TENSOR_FULL, cuda.ALGO_TENSOR, cuda.ALGO_AUTO):
         assert _find_device(cuda, m, needles, algo) == want, algo
     for thr in (0, 15, 36, 37, 50, 63):
         mt = cuda.CudaMatcher(db, thr)
         w = sorted(match_tuples(oracle.matcher_find(rows, needles, thr)))
         if q <= 8 or thr <= 37:        # 700 needles at thr 50+: every pair is a candidate, slow but covered at q = 8
             assert _find_device(cuda, mt, needles, cuda.ALGO_TENSOR_PREFIX, cap=1 << 18) == w, thr
+            assert _find_device(cuda, mt, needles, cuda.ALGO_TENSOR_PAIRED, cap=1 << 18) == w, thr
         assert _find_device(cuda, mt, needles, cuda.ALGO_TENSOR, cap=1 << 18) == w, thr
     db.close()
+
+
+@pytest.mark.parametrize("q", [5, 300])
+def test_paired_accumulator_fields(cuda, oracle, q):
+    """ALGO_TENSOR_PAIRED packs the prefix dot products of rows r and r + 240 (same 480-row group) into one f32
+    accumulator as two s16 fields.  Plant every combination of prefix distances in the two rows of one column --
+    including the ones that push the packed value out of its exponent window (prefix distance < 32 or > 96 in
+    the high row) and a negative low field that borrows from the high one -- and require the exact match set."""
+    rng = np.random.default_rng(77 + q)
+    n_rows = 960 * 40 + 123
+    rows = oracle.synth_db(n_rows, first_row=11)
+    needles = rng.integers(0, 256, size=(q, 32), dtype=np.uint8)
+    lo_cases = [(0, 0), (31, 0), (32, 0), (0, 31), (16, 15), (128, 0), (100, 3), (64, 0), (33, 0), (127, 0)]
+    hi_cases = [(0, 0), (31, 0), (32, 0), (0, 31), (16, 15), (128, 0), (97, 0), (96, 0), (30, 1), (1, 0), (127, 128)]
+    col = 0
+    for a in lo_cases:
+        for b in hi_cases:
+            group = (col * 7) % (n_rows // 480 - 1)
+            c = (col * 53) % 240
+            needle = needles[(col * 3) % q]
+            rows[group * 480 + c] = _flip_in(needle, a[0], a[1], rng)             # low field of the column
+            rows[group * 480 + 240 + c] = _flip_in(needle, b[0], b[1], rng)       # high field of the same column
+            col += 1
+    for thr in (31, 0, 36, 63):
+        want = sorted(match_tuples(oracle.matcher_find(rows, needles, thr)))
+        assert len(want) >= 4
+        m = cuda.CudaMatcher(cuda.CudaVectorDatabase(rows), thr)
+        if q <= 8 or thr <= 36:
+            assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_PAIRED, cap=1 << 18) == want, thr
+        assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_FULL, cap=1 << 18) == want, thr
 
 
 def test_adversarial_dense_matches(cuda, oracle):
@@ -182,7 +218,7 @@ def test_adversarial_dense_matches(cuda, oracle):
     got = m.find_all(needles, cap=1000)        # forces the E_CAPACITY retry path
     assert match_tuples(got) == want
     for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8, cuda.ALGO_TENSOR_FULL,
-                 cuda.ALGO_TENSOR_PREFIX):
+                 cuda.ALGO_TENSOR_PREFIX, cuda.ALGO_TENSOR_PAIRED):
         assert _find_device(cuda, m, needles, algo, cap=1 << 19) == sorted(want)
     assert _find_device(cuda, m, needles[:32], cuda.ALGO_STREAM, cap=1 << 19) == sorted(
         t for t in want if t[1] < 32)
@@ -247,7 +283,7 @@ def test_headline_config_10m(cuda, oracle):
     assert match_tuples(m.find_all(needles)) == want
     assert m.find_min(needles) == (want[0][0], want[0][1])
     for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_STREAM, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8,
-                 cuda.ALGO_TENSOR_FULL, cuda.ALGO_TENSOR_PREFIX):
+                 cuda.ALGO_TENSOR_FULL, cuda.ALGO_TENSOR_PREFIX, cuda.ALGO_TENSOR_PAIRED):
         assert _find_device(cuda, m, needles, algo) == want
     # last rows of the last chunk are planted too (tail handling)
     db.write_rows(n - 1, needles[5][None])

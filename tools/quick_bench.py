@@ -85,9 +85,9 @@ def main():
         m = yp.CudaMatcher(db, 31)
         out = torch.zeros((1 << 20, 16), dtype=torch.uint8, device="cuda")
         cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
-        for q in (1024, 4096, 32768):
+        for q in (512, 1024, 4096, 32768):
             needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
-            for name, algo in (("full", yp.ALGO_TENSOR_FULL), ("prefix", yp.ALGO_TENSOR_PREFIX)):
+            for name, algo in (("full", yp.ALGO_TENSOR_FULL), ("prefix", yp.ALGO_TENSOR_PREFIX), ("paired", yp.ALGO_TENSOR_PAIRED)):
                 med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 20, cnt, algo=algo), iters=5, warm=1)
                 print(f"[{tag}] match 10M x {q:6d} {name:6s}: median {med / 1e3:9.2f} ms  {n * q / med / 1e6:8.3f} Tpairs/s  "
                       f"hits={int(cnt.item())}")
@@ -95,10 +95,10 @@ def main():
         for thr in (36, 40):   # candidate-rate sensitivity of the prefix filter
             mt = yp.CudaMatcher(db, thr)
             needles = torch.from_numpy(rng.integers(0, 256, size=(32768, 32), dtype=np.uint8)).cuda()
-            med, best = timeit(lambda: mt.find_device(needles, 32768, out, 1 << 20, cnt, algo=yp.ALGO_TENSOR_PREFIX),
-                               iters=3, warm=1)
-            print(f"[{tag}] match 10M x  32768 prefix thr={thr}: median {med / 1e3:9.2f} ms  {n * 32768 / med / 1e6:8.3f} Tpairs/s")
-            cnt.zero_()
+            for name, algo in (("prefix", yp.ALGO_TENSOR_PREFIX), ("paired", yp.ALGO_TENSOR_PAIRED)):
+                med, best = timeit(lambda: mt.find_device(needles, 32768, out, 1 << 20, cnt, algo=algo), iters=3, warm=1)
+                print(f"[{tag}] match 10M x  32768 {name} thr={thr}: median {med / 1e3:9.2f} ms  {n * 32768 / med / 1e6:8.3f} Tpairs/s")
+                cnt.zero_()
         db.close()
     if "hashpx" in what:   # hash kernel per pixel format
         k = yp.CudaKernel(0)

@@ -29,7 +29,7 @@ LIB_PATH = os.environ.get("YUME_PDQ_CUDA_LIB") or os.path.join(HERE, "libyume_pd
 MATCH_DTYPE = np.dtype([("row", "<u8"), ("needle", "<u4"), ("dist", "<u4")])
 
 ALGO_AUTO, ALGO_EXACT, ALGO_TILED, ALGO_STREAM, ALGO_TENSOR, ALGO_TENSOR_I8 = 0, 1, 2, 3, 4, 5
-ALGO_TENSOR_FULL, ALGO_TENSOR_PREFIX = 6, 7
+ALGO_TENSOR_FULL, ALGO_TENSOR_PREFIX, ALGO_TENSOR_PAIRED = 6, 7, 8
 
 OP_T = 0
 OP_NEGATE_ALT_COLS_FALSE = 1

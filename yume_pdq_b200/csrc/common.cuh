@@ -84,6 +84,11 @@ int launch_match_tensor4(const uint8_t *rows, size_t n_rows, uint64_t row_offset
                          unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base = 0,
                          int prefix = -1);
 
+int launch_match_tensor4x2(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
+                           size_t q, uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
+                           unsigned long long *min_key, int mode, int sm_count, cudaStream_t s,
+                           uint32_t needle_base = 0);
+
 int launch_synth_frames(float *frames, size_t n, uint64_t first, uint64_t seed, int kind,
                         cudaStream_t s);
 int launch_synth_pixels(uint8_t *frames, int pixel_format, size_t n, uint64_t first, uint64_t seed,
