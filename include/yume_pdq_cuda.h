@@ -98,6 +98,11 @@ uint64_t yume_pdq_cuda_launch_count(void);
  * FLOPPED_ROTATED_270, ROTATED_90 (NORMAL + the visit order of lib.rs:358-420). */
 extern const uint32_t YUME_PDQ_CUDA_DIHEDRAL_ORDER[8];
 
+/* Page-locked host memory for callers without a CUDA runtime of their own (the `pipe` front end reads frames
+ * straight into it): host-pointer calls on such buffers copy at the full PCIe rate and overlap with kernels. */
+int yume_pdq_cuda_host_alloc(int device, size_t bytes, void **out);
+int yume_pdq_cuda_host_free(void *p);
+
 /* ---- hasher: fused hot path (hash_get_threshold + visit_dihedrals, batched) ----
  * frames   n x 512 x 512 f32
  * hashes   n x 8 x 32 bytes, dihedral order above          (required)

@@ -75,6 +75,8 @@ SIGNATURES = {
     "yume_pdq_cuda_error_string": (C.c_char_p, [C.c_int]),
     "yume_pdq_cuda_device_count": (C.c_int, []),
     "yume_pdq_cuda_kernel_ident": (C.c_char_p, []),
+    "yume_pdq_cuda_host_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "yume_pdq_cuda_host_free": (C.c_int, [C.c_void_p]),
     "yume_pdq_cuda_matcher_ident": (C.c_char_p, []),
     "yume_pdq_cuda_launch_count": (C.c_uint64, []),
     "yume_pdq_cuda_hash_batch": (C.c_int, [C.c_int, _vp, C.c_size_t, _vp, _vp, _vp, _vp, _vp]),

@@ -9,6 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libyume_pdq_cuda.so")
+CLI_SRC = os.path.join(HERE, "cli")
+CLI = os.path.join(HERE, "yume-pdq-cuda")     # `pipe` front end (cli/yume_pdq_pipe.cpp), links only the C ABI
 SOURCES = ["api.cu", "hasher.cu", "matcher.cu", "matcher_tc.cu", "matcher_tc4.cu", "matcher_tc4x2.cu", "synth.cu", "peak.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -44,8 +46,23 @@ def build_variant(tag: str, defines: list[str]) -> str:
     return out
 
 
+def build_cli(force: bool = False) -> str:
+    srcs = [os.path.join(CLI_SRC, f) for f in os.listdir(CLI_SRC)]
+    deps = srcs + [LIB, os.path.join(HERE, "..", "include", "yume_pdq_cuda.h")]
+    if not force and os.path.exists(CLI) and all(os.path.getmtime(d) <= os.path.getmtime(CLI) for d in deps):
+        return CLI
+    cmd = [shutil.which("g++") or "g++", "-O2", "-std=c++17", "-Wall", "-pthread",
+           os.path.join(CLI_SRC, "yume_pdq_pipe.cpp"), "-L" + HERE, "-lyume_pdq_cuda", "-Wl,-rpath,$ORIGIN", "-o", CLI]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("g++ failed (yume-pdq-cuda)")
+    return CLI
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
+        build_cli()
         return LIB
     cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -57,6 +74,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed")
     if verbose:
         print(log)
+    build_cli(force=True)
     return LIB
 
 

@@ -383,6 +383,31 @@ extern "C" {
 
 size_t yume_pdq_cuda_frame_bytes(int pixel_format) { return frame_bytes(pixel_format); }
 
+int yume_pdq_cuda_host_alloc(int device, size_t bytes, void **out)
+{
+    if (!out || bytes == 0)
+        return YUME_PDQ_CUDA_E_INVALID;
+    *out = nullptr;
+    const int rc = ensure_device(device);
+    if (rc != 0)
+        return rc;
+    const cudaError_t e = cudaMallocHost(out, bytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        *out = nullptr;
+        return e == cudaErrorMemoryAllocation ? YUME_PDQ_CUDA_E_NOMEM : (int)e;
+    }
+    return 0;
+}
+
+int yume_pdq_cuda_host_free(void *p)
+{
+    if (!p)
+        return 0;
+    YPDQ_CUDA_TRY(cudaFreeHost(p));
+    return 0;
+}
+
 int yume_pdq_cuda_hash_batch(int device, const float *frames, size_t n, uint8_t *hashes,
                              float *quality, float *thresholds, float *pdqf, void *stream)
 {
