@@ -210,6 +210,7 @@ def cpu_baseline_leg(args):
 
 # --------------------------------------------------------------------------
 def main():
+    global DB_ROWS, FRAMES_PER_GPU
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -219,7 +220,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help=argparse.SUPPRESS)
+    # BASELINE config 5 (INT/tensor regime): --db-rows 1000000000 --frames 128 on 8 GPUs (1024 images per batch)
+    ap.add_argument("--db-rows", type=int, default=DB_ROWS, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    DB_ROWS, FRAMES_PER_GPU = args.db_rows, args.frames
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
