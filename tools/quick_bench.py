@@ -100,6 +100,20 @@ def main():
                 print(f"[{tag}] match 10M x  32768 {name} thr={thr}: median {med / 1e3:9.2f} ms  {n * 32768 / med / 1e6:8.3f} Tpairs/s")
                 cnt.zero_()
         db.close()
+    if "x2" in what:   # paired tensor matcher only (developer variants: YUME_PDQ_CUDA_LIB=...)
+        tag = os.path.basename(os.environ.get("YUME_PDQ_CUDA_LIB", "default"))
+        n = (10_000_000 // 2048 + 1) * 2048
+        db = yp.CudaVectorDatabase(synthetic_rows=n)
+        m = yp.CudaMatcher(db, 31)
+        out = torch.zeros((1 << 20, 16), dtype=torch.uint8, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for q in (1024, 4096, 32768):
+            needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
+            med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 20, cnt, algo=yp.ALGO_TENSOR_PAIRED), iters=5, warm=1)
+            print(f"[{tag}] match 10M x {q:6d} paired: median {med / 1e3:9.2f} ms  {n * q / med / 1e6:8.3f} Tpairs/s  "
+                  f"hits={int(cnt.item())}")
+            cnt.zero_()
+        db.close()
     if "hashpx" in what:   # hash kernel per pixel format
         k = yp.CudaKernel(0)
         n = 4096

@@ -246,11 +246,18 @@ match_tensor4x2_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const ui
                         bar_wait(&d_empty[t], (ia & 1u) ^ 1u);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t d_addr = tmem + t * X2_N;
+#ifndef X2_EXPERIMENT_NO_BIAS     // developer timing experiment (wrong results): what would 4 MMAs per tile give?
                         mma(d_addr, d_bias_a, d_bias_b, tmem + X2_SF_BIAS, 0u);
+#endif
 #pragma unroll
                         for (uint32_t k = 0; k < 2; k++)
                             mma(d_addr, x2_desc(a_addr + k * 2 * X2_LBO, X2_SBO),
-                                x2_desc(b_addr + (2 * t + 1) * X2_B_BYTES + k * 2 * X2_LBO, X2_SBO), tmem + X2_SF_HI, 1u);
+                                x2_desc(b_addr + (2 * t + 1) * X2_B_BYTES + k * 2 * X2_LBO, X2_SBO), tmem + X2_SF_HI,
+#ifdef X2_EXPERIMENT_NO_BIAS
+                                k);
+#else
+                                1u);
+#endif
 #pragma unroll
                         for (uint32_t k = 0; k < 2; k++)
                             mma(d_addr, x2_desc(a_addr + k * 2 * X2_LBO, X2_SBO),
@@ -321,7 +328,14 @@ match_tensor4x2_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const ui
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     if (lane == 0)
                         bar_arrive_addr(dempty + 8 * acc);
+#ifdef X2_EXPERIMENT_NO_ARITH     // developer timing experiment: TMEM loads only
+#pragma unroll
+                    for (int j = 0; j < X2_EB; j++)
+                        asm volatile("" ::"r"(v[j]));
+                    if (false) {
+#else
                     if (x2_batch_any(v, lmin, hmin)) {
+#endif
                         // rare path: indices are rebuilt from opaque copies of the loop counters so that the
                         // compiler does not carry 64-bit row arithmetic through the hot loop
                         uint32_t si_ = si, m_ = m;
@@ -376,13 +390,18 @@ int launch_match_tensor4x2(const uint8_t *rows, size_t n_rows, uint64_t row_offs
     // in the window the high half reads 0x4B40 + dot_hi (- 1 on a borrow); from dot_hi = 64 on the exponent of Z
     // moves and the half reads 0x4B80 + (dot_hi - 64) / 2 (and the low half dot_lo / 2): flag all of those
     const int32_t hi_min = (int32_t)(std::min<uint32_t>((X2_BITS_BASE >> 16) + (uint32_t)dot_min - 1u, 0x4B80u) << 16);
+#ifdef X2_EXPERIMENT_NO_BIAS
+    const int32_t lo_min_ = 40000, hi_min_ = 0x7FFF0000;     // nothing is ever flagged: timing only
+#else
+    const int32_t lo_min_ = lo_min, hi_min_ = hi_min;
+#endif
     static bool attr_set = false;
     if (!attr_set) {
         YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor4x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X2_SMEM));
         attr_set = true;
     }
     match_tensor4x2_kernel<<<grid, X2_THREADS, X2_SMEM, s>>>(reinterpret_cast<const uint4 *>(rows), n_rows, exp, n_mtiles,
-                                                             (uint32_t)q, lo_min, hi_min, sink);
+                                                             (uint32_t)q, lo_min_, hi_min_, sink);
     YPDQ_LAUNCH_CHECK();
     YPDQ_CUDA_TRY(cudaFreeAsync(exp, s));
     return 0;
