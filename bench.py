@@ -380,19 +380,18 @@ def main():
         scan_bytes = shard_rows * 32
         share = m_mean / (m_mean + h_mean)
         # Tensor roofline.  At threshold <= 36 the matcher runs the 128-bit prefix filter on the tensor cores with two
-        # rows per accumulator column (match_tensor4x2_kernel): ALGORITHMIC work of one (row, needle) pair = 128
-        # multiply-adds = 256 ops of the packed-FP4 MMA (tcgen05.mma kind::mxf4, e2m1 +-1 operands, f32 accumulate)
-        # plus an exact POPC check of the rare candidates; the kernel EXECUTES 320 ops per pair (a fifth MMA per
-        # tile adds the constant that aligns the two s16 fields of the accumulator).  Above threshold 36 the full
-        # 256-bit dot product runs (match_tensor4_kernel), 512 ops.  `achieved` counts the algorithmic ops,
-        # `executed_frac` the ops the tensor pipe actually performs.  Peak: MEASURED_PEAKS.json holds a dense bf16
-        # rate but no FP4 one, and 4 x its bf16 figure (FP4 : bf16 = 4 : 1 on the tensor pipe) is BELOW what this
-        # kernel achieves (cuBLAS bf16 on random data is power-limited to ~1.4 GHz, +-1 operands are not), so the
-        # denominator is the issue rate of the very same instruction measured live on this GPU with no loads and no
-        # epilogue (yume_pdq_cuda_measure_mxf4_peak); the bf16-derived figure is kept beside it.
+        # rows per accumulator column (match_tensor4x2_kernel): one (row, needle) pair = 128 multiply-adds = 256 ops of
+        # the packed-FP4 MMA (tcgen05.mma kind::mxf4, e2m1 operands, f32 accumulate; in the high field 6 of the 128
+        # element positions carry the constant that aligns the two s16 fields, 122 carry hash bits) plus an exact
+        # POPC check of the rare candidates.  Above threshold 36 the full 256-bit dot product runs
+        # (match_tensor4_kernel), 512 ops.  Peak: MEASURED_PEAKS.json holds a dense bf16 rate but no FP4 one, and 4 x
+        # its bf16 figure (FP4 : bf16 = 4 : 1 on the tensor pipe) is BELOW what this kernel achieves (cuBLAS bf16 on
+        # random data is power-limited to ~1.4 GHz, +-1 operands are not), so the denominator is the issue rate of the
+        # very same instruction measured live on this GPU with no loads and no epilogue
+        # (yume_pdq_cuda_measure_mxf4_peak); the bf16-derived figure is kept beside it.
         paired = THRESHOLD <= 36
         ops_per_pair = 256 if paired else 512
-        executed_per_pair = 320 if paired else 512
+        executed_per_pair = 256 if paired else 512
         bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
         mxf4_peak, mxf4_clk = yp.measure_mxf4_peak(local_rank, 20000)
         achieved_tops = pairs * ops_per_pair / (m_mean * 1e-3) / 1e12

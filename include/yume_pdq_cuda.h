@@ -213,7 +213,7 @@ int yume_pdq_cuda_db_write_rows(YumePDQ_CudaDb *db, size_t first_local_row, cons
 #define YUME_PDQ_CUDA_ALGO_TENSOR_I8 5  /* tcgen05.mma kind::i8 on +-1 int8 expanded bits, any threshold */
 #define YUME_PDQ_CUDA_ALGO_TENSOR_FULL 6    /* kind::mxf4, always the full 256-bit dot product (threshold <= 127) */
 #define YUME_PDQ_CUDA_ALGO_TENSOR_PREFIX 7  /* kind::mxf4, always the 128-bit prefix filter (threshold <= 63) */
-#define YUME_PDQ_CUDA_ALGO_TENSOR_PAIRED 8  /* kind::mxf4, 128-bit prefix filter with two rows per f32 accumulator (s16x2 fields; threshold <= 63) */
+#define YUME_PDQ_CUDA_ALGO_TENSOR_PAIRED 8  /* kind::mxf4, 128-bit prefix filter with two rows per f32 accumulator (s16x2 fields; threshold <= 60) */
 
 /* PDQMatcher::scan (matching/mod.rs:72-79): *matched = 1 iff any needle is within
  * `threshold` (inclusive) of any row.  needles q x 32 bytes, host or device. */

@@ -69,6 +69,7 @@ def test_thresholds(cuda, oracle, threshold):
             assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_FULL, cap=1 << 18) == sorted(want)
         if threshold <= 63:    # beyond 36 nearly every pair is a candidate: slow, still exact
             assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_PREFIX, cap=1 << 18) == sorted(want)
+        if threshold <= 60:
             assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_PAIRED, cap=1 << 18) == sorted(want)
     db.close()
     # the forced variants reject thresholds they cannot represent instead of answering wrongly
@@ -155,7 +156,7 @@ def test_prefix_filter_boundaries(cuda, oracle, q):
             rows[pos[k]] = _flip_in(needles[(rep * 89 + 7 * k) % q], lo, hi, rng)
             k += 1
     # tile edges: last row of a 240-row tile / 480-row super-tile, first of the next, last row of the DB
-    for r in (239, 240, 479, 480, 719, 720, 959, 960, 1199, 1200, rows.shape[0] - 1):
+    for r in (127, 128, 239, 240, 255, 256, 367, 368, 479, 480, 735, 736, 847, 848, 959, 960, 1199, 1200, rows.shape[0] - 1):
         rows[r] = _flip_in(needles[r % q], 15, 16, rng)
     want = sorted(match_tuples(oracle.matcher_find(rows, needles, 31)))
     assert len(want) >= 8 * 5 + 5
@@ -168,39 +169,80 @@ def test_prefix_filter_boundaries(cuda, oracle, q):
         w = sorted(match_tuples(oracle.matcher_find(rows, needles, thr)))
         if q <= 8 or thr <= 37:        # 700 needles at thr 50+: every pair is a candidate, slow but covered at q = 8
             assert _find_device(cuda, mt, needles, cuda.ALGO_TENSOR_PREFIX, cap=1 << 18) == w, thr
-            assert _find_device(cuda, mt, needles, cuda.ALGO_TENSOR_PAIRED, cap=1 << 18) == w, thr
+            if thr <= 60:
+                assert _find_device(cuda, mt, needles, cuda.ALGO_TENSOR_PAIRED, cap=1 << 18) == w, thr
         assert _find_device(cuda, mt, needles, cuda.ALGO_TENSOR, cap=1 << 18) == w, thr
     db.close()
 
 
 @pytest.mark.parametrize("q", [5, 300])
 def test_paired_accumulator_fields(cuda, oracle, q):
-    """ALGO_TENSOR_PAIRED packs the prefix dot products of rows r and r + 240 (same 480-row group) into one f32
-    accumulator as two s16 fields.  Plant every combination of prefix distances in the two rows of one column --
-    including the ones that push the packed value out of its exponent window (prefix distance < 32 or > 96 in
-    the high row) and a negative low field that borrows from the high one -- and require the exact match set."""
+    """ALGO_TENSOR_PAIRED packs the prefix dot products of two rows of a 960-row super-tile into one f32 accumulator
+    as two s16 fields: rows c and c + W of a group of 2 W rows (W = 128, 112, 128, 112; groups start at 0, 256, 480,
+    736); the high field compares hash bits 6..127 only (bits 0..5 of byte 0 carry the bias constants).  Plant every
+    combination of prefix distances in the two rows of one column -- including the ones that push the packed value
+    out of its exponent window (prefix distance < 32 or > 96 in the high row), a negative low field that borrows
+    from the high one, and differences confined to the six bias positions -- and require the exact match set."""
     rng = np.random.default_rng(77 + q)
     n_rows = 960 * 40 + 123
     rows = oracle.synth_db(n_rows, first_row=11)
     needles = rng.integers(0, 256, size=(q, 32), dtype=np.uint8)
+    groups = [(0, 128), (256, 112), (480, 128), (736, 112)]
+
+    def flip_bias_bits(h, k):        # flip k of the six lowest bits of byte 0
+        out = h.copy()
+        out[0] ^= np.uint8(sum(1 << int(b) for b in rng.choice(6, size=k, replace=False)))
+        return out
+
     lo_cases = [(0, 0), (31, 0), (32, 0), (0, 31), (16, 15), (128, 0), (100, 3), (64, 0), (33, 0), (127, 0)]
-    hi_cases = [(0, 0), (31, 0), (32, 0), (0, 31), (16, 15), (128, 0), (97, 0), (96, 0), (30, 1), (1, 0), (127, 128)]
+    hi_cases = [(0, 0), (31, 0), (32, 0), (0, 31), (16, 15), (128, 0), (97, 0), (96, 0), (30, 1), (1, 0), (127, 128),
+                "bias6", "bias3+29", "bias6+26"]
     col = 0
     for a in lo_cases:
         for b in hi_cases:
-            group = (col * 7) % (n_rows // 480 - 1)
-            c = (col * 53) % 240
+            st = (col * 7) % (n_rows // 960 - 1)
+            g0, w = groups[col % 4]
+            c = (col * 53) % w
             needle = needles[(col * 3) % q]
-            rows[group * 480 + c] = _flip_in(needle, a[0], a[1], rng)             # low field of the column
-            rows[group * 480 + 240 + c] = _flip_in(needle, b[0], b[1], rng)       # high field of the same column
+            rows[st * 960 + g0 + c] = _flip_in(needle, a[0], a[1], rng)                 # low field of the column
+            if b == "bias6":            # distance 6, all of it invisible to the high field
+                hi = flip_bias_bits(needle, 6)
+            elif b == "bias3+29":       # distance 32: 3 invisible + 29 visible -> candidate, not a match
+                hi = flip_bias_bits(_flip_in(needle, 0, 29, rng), 3)
+            elif b == "bias6+26":       # distance 32 again, 26 visible
+                hi = flip_bias_bits(_flip_in(needle, 0, 26, rng), 6)
+            else:
+                hi = _flip_in(needle, b[0], b[1], rng)
+            rows[st * 960 + g0 + w + c] = hi                                            # high field of the same column
             col += 1
-    for thr in (31, 0, 36, 63):
+    for thr in (31, 0, 36, 60):
         want = sorted(match_tuples(oracle.matcher_find(rows, needles, thr)))
         assert len(want) >= 4
         m = cuda.CudaMatcher(cuda.CudaVectorDatabase(rows), thr)
         if q <= 8 or thr <= 36:
             assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_PAIRED, cap=1 << 18) == want, thr
         assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_FULL, cap=1 << 18) == want, thr
+
+
+def test_paired_needle_chunks(cuda, oracle):
+    """A small shard is cut along the needle axis too (work unit = super-tile x chunk of >= 32 needle tiles), which
+    is how an 8-GPU split of a 10M-row DB keeps 148 SMs busy: 12,365 needles (97 tiles -> 3 chunks) against 3,000 and
+    961 rows, matches planted in every chunk and at the chunk edges."""
+    rng = np.random.default_rng(99)
+    q = 3 * 32 * 128 + 77
+    needles = rng.integers(0, 256, size=(q, 32), dtype=np.uint8)
+    for n_rows in (3000, 961):
+        rows = oracle.synth_db(n_rows, first_row=3)
+        sel = np.concatenate([rng.choice(q, size=150, replace=False),
+                              [0, 33 * 128 - 1, 33 * 128, 66 * 128 - 1, 66 * 128, q - 1]])
+        pos = rng.choice(n_rows, size=len(sel), replace=False)
+        for j, r in zip(sel, pos):
+            rows[r] = flip_bits(needles[j], int(rng.integers(0, 34)), rng)
+        want = sorted(match_tuples(oracle.matcher_find(rows, needles, 31)))
+        assert len(want) > 100
+        m = cuda.CudaMatcher(cuda.CudaVectorDatabase(rows), 31)
+        assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_PAIRED) == want
+        assert _find_device(cuda, m, needles, cuda.ALGO_AUTO) == want
 
 
 def test_adversarial_dense_matches(cuda, oracle):
