@@ -10,6 +10,11 @@ pub struct YumePDQ_CudaDb { _private: [u8; 0] }
 pub struct YumePDQ_Match { pub row: u64, pub needle: u32, pub dist: u32 }
 
 pub const E_CAPACITY: c_int = -3;
+pub const PIXEL_F32: c_int = 0;
+pub const PIXEL_LUMA8: c_int = 1;
+pub const PIXEL_RGB8: c_int = 2;
+pub const PIXEL_RGBA8: c_int = 3;
+pub const PIXEL_FMA: c_int = 0x100;
 
 unsafe extern "C" {
     pub fn yume_pdq_cuda_error_string(code: c_int) -> *const c_char;
@@ -17,6 +22,12 @@ unsafe extern "C" {
     pub fn yume_pdq_cuda_kernel_ident() -> *const c_char;
     pub fn yume_pdq_cuda_hash_batch(device: c_int, frames: *const f32, n: usize, hashes: *mut u8,
         quality: *mut f32, thresholds: *mut f32, pdqf: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn yume_pdq_cuda_hash_batch_pixels(device: c_int, frames: *const c_void, pixel_format: c_int, n: usize,
+        hashes: *mut u8, quality: *mut f32, thresholds: *mut f32, pdqf: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn yume_pdq_cuda_cvt_to_luma8f(device: c_int, pixels: *const c_void, pixel_format: c_int, n_pixels: usize,
+        coeff: *const f32, out: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn yume_pdq_cuda_host_alloc(device: c_int, bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn yume_pdq_cuda_host_free(p: *mut c_void) -> c_int;
     pub fn yume_pdq_cuda_jarosz_compress(device: c_int, frames: *const f32, n: usize, buf1: *mut f32,
         stream: *mut c_void) -> c_int;
     pub fn yume_pdq_cuda_dct2d(device: c_int, buf1: *const f32, n: usize, pdqf: *mut f32,
@@ -35,4 +46,8 @@ unsafe extern "C" {
         matched: *mut c_int, stream: *mut c_void) -> c_int;
     pub fn yume_pdq_cuda_matcher_find(db: *mut YumePDQ_CudaDb, needles: *const u8, q: usize, threshold: u32,
         out: *mut YumePDQ_Match, cap: usize, n_found: *mut usize, stream: *mut c_void) -> c_int;
+    /// hash + 8 dihedrals + match for a whole batch (examples/end_to_end.rs:224-256 in one pipelined call)
+    pub fn yume_pdq_cuda_screen_batch_pixels(db: *mut YumePDQ_CudaDb, frames: *const c_void, pixel_format: c_int,
+        n: usize, threshold: u32, hashes: *mut u8, quality: *mut f32, out: *mut YumePDQ_Match, cap: usize,
+        n_found: *mut usize, stream: *mut c_void) -> c_int;
 }

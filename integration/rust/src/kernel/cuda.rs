@@ -31,6 +31,21 @@ impl CudaKernel {
         ok(unsafe { sys::yume_pdq_cuda_hash_batch(self.device, frames.as_ptr(), n, hashes.as_mut_ptr(),
             quality.as_mut_ptr(), thresholds.as_mut_ptr(), core::ptr::null_mut(), core::ptr::null_mut()) }, "hash_batch");
     }
+    /// The same for raw 8-bit frames (`sys::PIXEL_LUMA8 / RGB8 / RGBA8`): the input conversion of the CLI
+    /// (main.rs:486-608) runs inside the hash kernel, a frame crosses PCIe as bytes.
+    pub fn hash_batch_pixels(&self, frames: &[u8], pixel_format: i32, hashes: &mut [u8], quality: &mut [f32],
+                             thresholds: &mut [f32]) {
+        let channels = match pixel_format & 0xff { sys::PIXEL_LUMA8 => 1, sys::PIXEL_RGB8 => 3, _ => 4 };
+        let n = frames.len() / (512 * 512 * channels);
+        assert!(hashes.len() == n * 256 && quality.len() == n * 8 && thresholds.len() == n * 8);
+        ok(unsafe { sys::yume_pdq_cuda_hash_batch_pixels(self.device, frames.as_ptr().cast(), pixel_format, n,
+            hashes.as_mut_ptr(), quality.as_mut_ptr(), thresholds.as_mut_ptr(), core::ptr::null_mut(),
+            core::ptr::null_mut()) }, "hash_batch_pixels");
+    }
+    fn cvt(&self, pixels: *const core::ffi::c_void, fmt: i32, n: usize, coeff: [f32; 3], out: *mut f32) {
+        ok(unsafe { sys::yume_pdq_cuda_cvt_to_luma8f(self.device, pixels, fmt, n, coeff.as_ptr(), out,
+            core::ptr::null_mut()) }, "cvt_to_luma8f");
+    }
     fn transform(&self, p: &mut GenericArray<GenericArray<f32, U16>, U16>, op: i32) {
         ok(unsafe { sys::yume_pdq_cuda_pdqf_transform(self.device, p.as_mut_ptr().cast(), 1, op, core::ptr::null_mut()) }, "pdqf_transform");
     }
@@ -47,6 +62,20 @@ impl Kernel for CudaKernel {
 
     fn ident(&self) -> &'static str { "cuda_sm100a_f32_bitexact_scalar_order" }
     fn adjust_quality(input: f32) -> f32 { (input / super::QUALITY_ADJUST_DIVISOR as f32).min(1.0) }
+
+    // mod.rs:303-340: the coefficients arrive as f32 bit patterns in const generics
+    fn cvt_rgb8_to_luma8f<const R_COEFF: u32, const G_COEFF: u32, const B_COEFF: u32>(
+        &mut self, input: &GenericArray<GenericArray<u8, generic_array::typenum::U3>, U512>,
+        output: &mut GenericArray<f32, U512>) {
+        self.cvt(input.as_ptr().cast(), sys::PIXEL_RGB8, 512,
+                 [f32::from_bits(R_COEFF), f32::from_bits(G_COEFF), f32::from_bits(B_COEFF)], output.as_mut_ptr());
+    }
+    fn cvt_rgba8_to_luma8f<const R_COEFF: u32, const G_COEFF: u32, const B_COEFF: u32>(
+        &mut self, input: &GenericArray<GenericArray<u8, generic_array::typenum::U4>, U512>,
+        output: &mut GenericArray<f32, U512>) {
+        self.cvt(input.as_ptr().cast(), sys::PIXEL_RGBA8, 512,
+                 [f32::from_bits(R_COEFF), f32::from_bits(G_COEFF), f32::from_bits(B_COEFF)], output.as_mut_ptr());
+    }
 
     fn jarosz_compress(&mut self, buffer: &GenericArray<GenericArray<f32, U512>, U512>,
                        output: &mut GenericArray<GenericArray<f32, U128>, U128>) {
