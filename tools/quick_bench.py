@@ -113,6 +113,11 @@ def main():
             print(f"[{tag}] match 10M x {q:6d} paired: median {med / 1e3:9.2f} ms  {n * q / med / 1e6:8.3f} Tpairs/s  "
                   f"hits={int(cnt.item())}")
             cnt.zero_()
+        for thr in (33, 36, 40):
+            mt = yp.CudaMatcher(db, thr)
+            med, best = timeit(lambda: mt.find_device(needles, 32768, out, 1 << 20, cnt, algo=yp.ALGO_TENSOR_PAIRED), iters=3, warm=1)
+            print(f"[{tag}] match 10M x  32768 paired thr={thr}: median {med / 1e3:9.2f} ms  {n * 32768 / med / 1e6:8.3f} Tpairs/s")
+            cnt.zero_()
         db.close()
     if "hashpx" in what:   # hash kernel per pixel format
         k = yp.CudaKernel(0)

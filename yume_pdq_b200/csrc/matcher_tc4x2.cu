@@ -20,13 +20,14 @@
 // lower bound of the distance, and flagged columns are re-checked on the packed bits (both rows, full 256-bit
 // distance), so the reported set is exact; no match can be lost.
 //
-// Persistent kernel, one CTA per SM, 12 warps.  A work unit is (960-row super-tile, chunk of needle tiles); units
+// Persistent kernel, one CTA per SM, 16 warps.  A work unit is (960-row super-tile, chunk of needle tiles); units
 // are dealt round-robin to the CTAs, chunk-major so that all CTAs stream the same needle tiles from L2.
-//   warps 8-9  expand the unit's 960 rows (first 16 bytes of each) into 4 e2m1 row tiles (double buffered)
-//   warp 10    streams the pre-expanded needle tiles (12 KB) through a 4-stage cp.async.bulk ring
-//   warp 11    issues the MMAs: two accumulator stages of 240 TMEM columns, 4 MMAs (M 128, N 240, K 64) each
-//   warps 0-7  epilogue: TMEM lane quadrant = warp % 4, column half = warp / 4: tcgen05.ld of 120 columns, hand the
-//              stage back, then the max tree.  LDTM moves 64 B/clk per sub-partition = 480 clk per 240-column stage,
+//   warps 12-13 expand the unit's 960 rows (first 16 bytes of each) into 4 e2m1 row tiles (double buffered)
+//   warp 14    streams the pre-expanded needle tiles (12 KB) through a 4-stage cp.async.bulk ring
+//   warp 15    issues the MMAs: two accumulator stages of 240 TMEM columns, 4 MMAs (M 128, N 240, K 64) each
+//   warps 0-11 epilogue: TMEM lane quadrant = warp % 4, column third = warp / 4: tcgen05.ld of 80 columns, hand the
+//              stage back, then the max tree; flagged columns go to a candidate list that verify_candidates_kernel
+//              checks on the packed bits after the scan.  LDTM moves 64 B/clk per sub-partition = 480 clk per 240-column stage,
 //              the same as the MMA time of 4 x 120 clk; the two warps of a scheduler drift apart, so most of one
 //              warp's max tree overlaps the other's TMEM read.  Tried and rejected on a B200: four stages of
 //              128 / 112 columns with the warps of a scheduler on different stages (N = 128 MMAs re-read the needle
@@ -70,7 +71,10 @@ constexpr uint32_t X2_LBO = 128;               // bytes between K-adjacent 16-by
 constexpr uint32_t X2_A_SBO = X2_A_CHUNKS_CFG * 128;
 constexpr int X2_A_BYTES = (X2_M / 8) * X2_A_SBO;     // 12 KB
 constexpr int X2_A_STAGES = 4;
-constexpr int X2_EPI_WARPS = 8;
+#ifndef X2_EPI_WARPS_CFG
+#define X2_EPI_WARPS_CFG 12
+#endif
+constexpr int X2_EPI_WARPS = X2_EPI_WARPS_CFG;   // accumulator columns per warp: 8 -> 120, 12 -> 80, 16 -> 60 (measured: 29.2 / 29.9 / 28.2e12 pairs/s)
 constexpr int X2_EXP_THREADS = 64;
 constexpr int X2_WARP_PRODUCER = X2_EPI_WARPS + 2, X2_WARP_MMA = X2_EPI_WARPS + 3;
 constexpr int X2_THREADS = 64 + X2_EXP_THREADS + 32 * X2_EPI_WARPS;
@@ -87,7 +91,7 @@ constexpr uint32_t X2_ROW_BIAS = 0x00777777u, X2_NEEDLE_BIAS = 0x00477777u;   //
 constexpr size_t X2_SMEM = 2 * (size_t)X2_SB_BYTES + X2_A_STAGES * (size_t)X2_A_BYTES + 256;
 constexpr int X2_MIN_CHUNK_TILES = 32;               // needle tiles per work unit, at least (amortises the row expansion)
 
-constexpr int X2_EB = X2_N / 2;                // 120 accumulator columns per epilogue warp
+constexpr int X2_EB = X2_N / (X2_EPI_WARPS / 4);   // accumulator columns per epilogue warp
 // block-scaled instruction descriptor: A = B = e2m1, both K-major, ue8m0 scales, dense K = 64
 constexpr uint32_t X2_IDESC = (1u << 7) | (1u << 10) | ((uint32_t)(X2_N >> 3) << 17) | (1u << 23) | ((uint32_t)(X2_M >> 4) << 24);
 
@@ -130,11 +134,21 @@ expand_needles_x2_kernel(const uint4 *__restrict__ needles, uint32_t q, uint8_t 
 template <int W>
 __device__ __forceinline__ void x2_load(int32_t (&v)[W], uint32_t taddr)
 {
-    static_assert(W == 120, "120 columns per warp");
-    T4_LD_X64(v, 0, taddr);
-    T4_LD_X32(v, 64, taddr + 64);
-    T4_LD_X16(v, 96, taddr + 96);
-    T4_LD_X8(v, 112, taddr + 112);
+    static_assert(W == 120 || W == 80 || W == 60, "120, 80 or 60 columns per warp");
+    if constexpr (W == 80) {
+        T4_LD_X64(v, 0, taddr);
+        T4_LD_X16(v, 64, taddr + 64);
+    } else if constexpr (W == 120) {
+        T4_LD_X64(v, 0, taddr);
+        T4_LD_X32(v, 64, taddr + 64);
+        T4_LD_X16(v, 96, taddr + 96);
+        T4_LD_X8(v, 112, taddr + 112);
+    } else {
+        T4_LD_X32(v, 0, taddr);
+        T4_LD_X16(v, 32, taddr + 32);
+        T4_LD_X8(v, 48, taddr + 48);
+        T4_LD_X4(v, 56, taddr + 56);
+    }
 }
 
 // May some column hold a prefix dot product that reaches its minimum in either field?  lo_min = 128 - 2 thr,
@@ -151,35 +165,84 @@ __device__ __forceinline__ bool x2_any(const int32_t (&v)[W], int32_t lo_min, in
     return ((int32_t)(int16_t)(m & 0xFFFFu) >= lo_min) | ((int32_t)m >= hi_min);
 }
 
-// rare path: verify both rows of every flagged column on the packed bits
+// Candidates of the prefix filter are not verified by the epilogue warp that finds them (an atomic or two dependent
+// global loads per candidate would hold up the warp, and with it the accumulator stage, for a microsecond): every
+// epilogue warp appends them to a private region of a list in global memory -- no atomics, the fill count lives in a
+// register -- and verify_candidates_kernel works the regions off after the scan.  A warp whose region is full
+// verifies inline, so nothing is ever dropped.
+struct X2Candidate {
+    uint64_t row;      // local row
+    uint32_t needle;
+    uint32_t pad;
+};
+constexpr uint32_t X2_CAND_SLOTS = 1024;   // per epilogue warp
+struct X2CandList {
+    X2Candidate *items;     // [gridDim.x * X2_EPI_WARPS][X2_CAND_SLOTS]
+    uint32_t *counts;       // [gridDim.x * X2_EPI_WARPS]
+};
+
+__device__ __forceinline__ void x2_verify(uint64_t row, uint32_t needle, const uint4 *__restrict__ rows, const Tc4Sink &sink)
+{
+    const uint4 b0 = __ldg(sink.needles_raw + 2 * (size_t)needle), b1 = __ldg(sink.needles_raw + 2 * (size_t)needle + 1);
+    const uint4 a0 = __ldg(rows + 2 * row), a1 = __ldg(rows + 2 * row + 1);
+    const uint32_t dist = hamming256(a0, a1, b0, b1);
+    if (dist <= sink.threshold)
+        tc4_emit(sink, row, needle, dist);
+}
+
+// rare path, entered by the whole warp: both rows of every flagged column of every lane become candidates
 template <int W>
 __device__ __forceinline__ void x2_report(const int32_t (&v)[W], int32_t lo_min, int32_t hi_min, uint64_t row0, uint64_t n_rows,
-                                       uint32_t needle, const uint4 *__restrict__ rows, const Tc4Sink &sink)
+                                          uint32_t needle, bool needle_ok, uint32_t lane, const uint4 *__restrict__ rows,
+                                          const Tc4Sink &sink, X2Candidate *region, uint32_t &n_cand)
 {
-    const uint4 b0 = __ldg(sink.needles_raw + 2 * (size_t)needle);
-    const uint4 b1 = __ldg(sink.needles_raw + 2 * (size_t)needle + 1);
+    static_assert(W % 8 == 0, "groups of 8 columns");
 #pragma unroll
     for (int w = 0; w < W / 8; w++) {
-        uint32_t mw = 0;
+        // group test first (4 instructions): a flagged warp spends most of this function skipping clean groups
+        const uint32_t g = __vimax3_s16x2(__vimax3_s16x2((uint32_t)v[8 * w], (uint32_t)v[8 * w + 1], (uint32_t)v[8 * w + 2]),
+                                          __vimax3_s16x2((uint32_t)v[8 * w + 3], (uint32_t)v[8 * w + 4], (uint32_t)v[8 * w + 5]),
+                                          __vmaxs2((uint32_t)v[8 * w + 6], (uint32_t)v[8 * w + 7]));
+        const bool flagged = needle_ok && (((int32_t)(int16_t)(g & 0xFFFFu) >= lo_min) | ((int32_t)g >= hi_min));
+        if (!__any_sync(0xFFFFFFFFu, flagged))
+            continue;
+        uint32_t mw = 0;     // bit j: column 8 w + j of this lane is flagged
+        if (flagged) {
 #pragma unroll
-        for (int j = 0; j < 8; j++)
-            mw |= (uint32_t)(((int32_t)(int16_t)(v[8 * w + j] & 0xFFFF) >= lo_min) | (v[8 * w + j] >= hi_min)) << j;
+            for (int j = 0; j < 8; j++)
+                mw |= (uint32_t)(((int32_t)(int16_t)(v[8 * w + j] & 0xFFFF) >= lo_min) | (v[8 * w + j] >= hi_min)) << j;
+        }
 #pragma unroll 1
-        while (mw) {
-            const uint64_t col_row = row0 + 8 * w + (__ffs(mw) - 1);
+        while (__any_sync(0xFFFFFFFFu, mw != 0)) {
+            const bool have = mw != 0;
+            const uint64_t col_row = row0 + 8 * w + (have ? __ffs(mw) - 1 : 0);
             mw &= mw - 1;
 #pragma unroll 1
             for (uint32_t f = 0; f < 2; f++) {
                 const uint64_t row = col_row + f * X2_N;  // low field: the stage's first 240 rows, high field: the next 240
-                if (row >= n_rows)
-                    continue;
-                const uint4 a0 = __ldg(rows + 2 * row), a1 = __ldg(rows + 2 * row + 1);
-                const uint32_t dist = hamming256(a0, a1, b0, b1);
-                if (dist <= sink.threshold)
-                    tc4_emit(sink, row, needle, dist);
+                const bool cand = have && row < n_rows;
+                const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, cand);
+                const uint32_t slot = n_cand + __popc(ballot & ((1u << lane) - 1u));
+                n_cand += __popc(ballot);
+                if (cand) {
+                    if (slot < X2_CAND_SLOTS)
+                        region[slot] = X2Candidate{row, needle, 0u};
+                    else
+                        x2_verify(row, needle, rows, sink);
+                }
             }
         }
     }
+}
+
+// one CTA per candidate region (= epilogue warp of the scan)
+__global__ void __launch_bounds__(128)
+verify_candidates_kernel(const uint4 *__restrict__ rows, X2CandList cand, Tc4Sink sink)
+{
+    const uint32_t n = min(cand.counts[blockIdx.x], X2_CAND_SLOTS);
+    const X2Candidate *region = cand.items + (size_t)blockIdx.x * X2_CAND_SLOTS;
+    for (uint32_t i = threadIdx.x; i < n; i += 128)
+        x2_verify(region[i].row, region[i].needle, rows, sink);
 }
 
 // Work units (super-tile, needle tile range), dealt round-robin to the CTAs in chunk-major order.  Every role of a
@@ -209,15 +272,20 @@ struct X2Cursor {
     __device__ __forceinline__ uint32_t m1(const X2Units &u) const { return min(u.n_mtiles, (ch + 1) * u.chunk_tiles); }
 };
 
-// Epilogue of one warp: TMEM lanes 32 quad .. 32 quad + 31 (needles), columns 120 part .. 120 part + 119 of both stages
+// Epilogue of one warp: TMEM lanes 32 quad .. 32 quad + 31 (needles), columns X2_EB part .. X2_EB part + X2_EB - 1 of
+// both stages
 __device__ __forceinline__ void x2_epilogue(uint32_t tmem, uint32_t quad, uint32_t part, uint32_t lane, uint64_t *d_full,
                                             uint64_t *d_empty, const X2Units &units, uint32_t q, int32_t lo_min, int32_t hi_min,
-                                            uint64_t n_rows, const uint4 *__restrict__ rows, const Tc4Sink &sink)
+                                            uint64_t n_rows, const uint4 *__restrict__ rows, const Tc4Sink &sink,
+                                            const X2CandList &cand)
 {
     uint32_t dfull = s32(&d_full[0]), dempty = s32(&d_empty[0]);
     uint32_t tbase = tmem + ((quad * 32u) << 16) + part * X2_EB;
     int32_t lmin = lo_min, hmin = hi_min;
     asm volatile("" : "+r"(dfull), "+r"(dempty), "+r"(tbase), "+r"(lmin), "+r"(hmin));   // keep them in registers
+    const uint32_t region_id = blockIdx.x * X2_EPI_WARPS + part * 4 + quad;
+    X2Candidate *region = cand.items + (size_t)region_id * X2_CAND_SLOTS;
+    uint32_t n_cand = 0;
     int32_t v[X2_EB];
     uint32_t parity = 0;
     for (X2Cursor c(units); c.valid(units); c.next(units)) {
@@ -234,24 +302,25 @@ __device__ __forceinline__ void x2_epilogue(uint32_t tmem, uint32_t quad, uint32
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 if (lane == 0)
                     bar_arrive_addr(dempty + 8 * acc);
-                if (x2_any<X2_EB>(v, lmin, hmin)) {
+                if (__any_sync(0xFFFFFFFFu, x2_any<X2_EB>(v, lmin, hmin))) {
                     // rare path; opaque copies keep the 64-bit row arithmetic out of the hot loop
                     uint32_t m_ = m;
                     asm volatile("" : "+r"(m_));
                     const uint32_t needle = m_ * X2_M + quad * 32 + lane;
-                    if (needle < q)
-                        x2_report<X2_EB>(v, lo_min, hi_min, st * X2_ROWS + acc * (2 * X2_N) + part * X2_EB, n_rows, needle,
-                                         rows, sink);
+                    x2_report<X2_EB>(v, lo_min, hi_min, st * X2_ROWS + acc * (2 * X2_N) + part * X2_EB, n_rows, needle,
+                                     needle < q, lane, rows, sink, region, n_cand);
                 }
             }
             parity ^= 1u;
         }
     }
+    if (lane == 0)
+        cand.counts[region_id] = n_cand;
 }
 
 __global__ void __launch_bounds__(X2_THREADS, 1)
 match_tensor4x2_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint8_t *__restrict__ needles_exp,
-                       X2Units units, uint32_t q, int32_t lo_min, int32_t hi_min, Tc4Sink sink)
+                       X2Units units, uint32_t q, int32_t lo_min, int32_t hi_min, Tc4Sink sink, X2CandList cand)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sB = smem;                                      // 2 x 60 KB
@@ -363,44 +432,43 @@ match_tensor4x2_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const ui
             }
         }
     } else if (warp >= X2_EPI_WARPS) {
-        // ===== row expanders: 64 threads, thread t expands rows t, t+64, ... of the super-tile, 4 rows at a time =====
+        // ===== row expanders: 64 threads, thread t expands rows t, t+64, ... of the super-tile =====
         const uint32_t t = threadIdx.x - 32 * X2_EPI_WARPS;
         uint32_t i = 0;
         for (X2Cursor c(units); c.valid(units); c.next(units), i++) {
             const uint64_t st = c.st;
             const uint32_t b = i & 1u;
             uint8_t *buf = sB + (size_t)b * X2_SB_BYTES;
-#pragma unroll 1
-            for (uint32_t g = 0; g < (X2_ROWS + 4 * X2_EXP_THREADS - 1) / (4 * X2_EXP_THREADS); g++) {
-                uint4 lo[4];
+            // all of the thread's rows are requested before the first one is used: with one HBM round trip per group
+            // of four the expansion of a super-tile took longer than the MMAs of an 8-needle-tile unit (q = 1024)
+            constexpr uint32_t PER_THREAD = (X2_ROWS + X2_EXP_THREADS - 1) / X2_EXP_THREADS;     // 15
+            uint4 lo[PER_THREAD];
 #pragma unroll
-                for (uint32_t h = 0; h < 4; h++) {  // loads first: the HBM latency overlaps the wait for the buffer
-                    const uint32_t r = t + X2_EXP_THREADS * (4 * g + h);
-                    const uint64_t row = st * X2_ROWS + r;
-                    lo[h] = make_uint4(0, 0, 0, 0);
-                    if (r < X2_ROWS && row < n_rows)
-                        lo[h] = __ldg(rows + 2 * row);
-                }
-                if (g == 0)
-                    bar_wait(&b_empty[b], ((i >> 1) & 1u) ^ 1u);
+            for (uint32_t h = 0; h < PER_THREAD; h++) {
+                const uint32_t r = t + X2_EXP_THREADS * h;
+                const uint64_t row = st * X2_ROWS + r;
+                lo[h] = make_uint4(0, 0, 0, 0);
+                if (r < X2_ROWS && row < n_rows)
+                    lo[h] = __ldg(rows + 2 * row);
+            }
+            bar_wait(&b_empty[b], ((i >> 1) & 1u) ^ 1u);
 #pragma unroll
-                for (uint32_t h = 0; h < 4; h++) {
-                    const uint32_t r = t + X2_EXP_THREADS * (4 * g + h);
-                    if (r < X2_ROWS) {
-                        // super-tile rows: stage 0 = [0, 480): 240 low + 240 high, stage 1 = [480, 960) the same; a
-                        // tile of 240 rows is 240 x 64 bytes in the canonical layout
-                        const uint32_t rr = r % X2_N;                                             // row within its tile
-                        const bool high = (r / X2_N) & 1u;
-                        uint8_t *tile = buf + (size_t)(r - rr) * X2_ROW_BYTES;                     // tiles are contiguous
-                        uint4 c0 = expand32(lo[h].x);
-                        if (high)
-                            c0.x = (c0.x & 0xFF000000u) | X2_ROW_BIAS;
-                        uint8_t *p = tile + (rr >> 3) * X2_SBO + (rr & 7u) * 16u;
-                        *reinterpret_cast<uint4 *>(p) = c0;
-                        *reinterpret_cast<uint4 *>(p + X2_LBO) = expand32(lo[h].y);
-                        *reinterpret_cast<uint4 *>(p + 2 * X2_LBO) = expand32(lo[h].z);
-                        *reinterpret_cast<uint4 *>(p + 3 * X2_LBO) = expand32(lo[h].w);
-                    }
+            for (uint32_t h = 0; h < PER_THREAD; h++) {
+                const uint32_t r = t + X2_EXP_THREADS * h;
+                if (r < X2_ROWS) {
+                    // super-tile rows: stage 0 = [0, 480): 240 low + 240 high, stage 1 = [480, 960) the same; a
+                    // tile of 240 rows is 240 x 64 bytes in the canonical layout
+                    const uint32_t rr = r % X2_N;                                             // row within its tile
+                    const bool high = (r / X2_N) & 1u;
+                    uint8_t *tile = buf + (size_t)(r - rr) * X2_ROW_BYTES;                     // tiles are contiguous
+                    uint4 c0 = expand32(lo[h].x);
+                    if (high)
+                        c0.x = (c0.x & 0xFF000000u) | X2_ROW_BIAS;
+                    uint8_t *p = tile + (rr >> 3) * X2_SBO + (rr & 7u) * 16u;
+                    *reinterpret_cast<uint4 *>(p) = c0;
+                    *reinterpret_cast<uint4 *>(p + X2_LBO) = expand32(lo[h].y);
+                    *reinterpret_cast<uint4 *>(p + 2 * X2_LBO) = expand32(lo[h].z);
+                    *reinterpret_cast<uint4 *>(p + 3 * X2_LBO) = expand32(lo[h].w);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
@@ -408,7 +476,7 @@ match_tensor4x2_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const ui
         }
     } else {
         x2_epilogue(tmem, (uint32_t)warp & 3u, (uint32_t)warp >> 2, (uint32_t)lane, d_full, d_empty, units, q, lo_min, hi_min,
-                    n_rows, rows, sink);
+                    n_rows, rows, sink, cand);
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -431,16 +499,6 @@ int launch_match_tensor4x2(const uint8_t *rows, size_t n_rows, uint64_t row_offs
     Tc4Sink sink{out, cap, count, min_key, row_offset, (uint64_t)q, mode, needle_base,
                  reinterpret_cast<const uint4 *>(needles), threshold};
     const uint32_t n_mtiles = (uint32_t)((q + X2_M - 1) / X2_M);
-    uint8_t *exp = nullptr;
-    cudaError_t e = cudaMallocAsync(&exp, (size_t)n_mtiles * X2_A_BYTES, s);
-    if (e != cudaSuccess) {
-        (void)cudaGetLastError();
-        return e == cudaErrorMemoryAllocation ? YUME_PDQ_CUDA_E_NOMEM : (int)e;
-    }
-    const uint32_t threads = n_mtiles * X2_M;
-    expand_needles_x2_kernel<<<(threads + 255) / 256, 256, 0, s>>>(reinterpret_cast<const uint4 *>(needles), (uint32_t)q, exp,
-                                                                   n_mtiles);
-    YPDQ_LAUNCH_CHECK();
     // Work units: a small shard (a 10M-row DB split over 8 GPUs is 1302 super-tiles for 148 SMs) is cut along the
     // needle axis as well, until there are >= 64 units per SM or a unit is down to X2_MIN_CHUNK_TILES needle tiles.
     X2Units units;
@@ -452,6 +510,20 @@ int launch_match_tensor4x2(const uint8_t *rows, size_t n_rows, uint64_t row_offs
     units.chunk_tiles = (n_mtiles + n_chunks - 1) / n_chunks;
     units.n_chunks = (n_mtiles + units.chunk_tiles - 1) / units.chunk_tiles;
     const unsigned grid = (unsigned)std::min<uint64_t>(units.n_stiles * units.n_chunks, (uint64_t)sm_count);
+    // one stream-ordered scratch block: expanded needle tiles | candidate counts | candidate regions
+    const size_t exp_bytes = (size_t)n_mtiles * X2_A_BYTES;
+    const size_t n_regions = (size_t)grid * X2_EPI_WARPS, count_bytes = (n_regions * 4 + 255) / 256 * 256;
+    uint8_t *exp = nullptr;
+    cudaError_t e = cudaMallocAsync(&exp, exp_bytes + count_bytes + n_regions * X2_CAND_SLOTS * sizeof(X2Candidate), s);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? YUME_PDQ_CUDA_E_NOMEM : (int)e;
+    }
+    X2CandList cand{reinterpret_cast<X2Candidate *>(exp + exp_bytes + count_bytes), reinterpret_cast<uint32_t *>(exp + exp_bytes)};
+    const uint32_t threads = n_mtiles * X2_M;
+    expand_needles_x2_kernel<<<(threads + 255) / 256, 256, 0, s>>>(reinterpret_cast<const uint4 *>(needles), (uint32_t)q, exp,
+                                                                   n_mtiles);
+    YPDQ_LAUNCH_CHECK();
     const int32_t lo_min = 128 - 2 * (int32_t)threshold;
     const int32_t hi_dot_min = X2_HI_BITS - 2 * (int32_t)threshold;
     // in the window the high half reads 0x4B40 + dot_hi (- 1 on a borrow); from dot_hi = 64 on the exponent of Z
@@ -468,7 +540,9 @@ int launch_match_tensor4x2(const uint8_t *rows, size_t n_rows, uint64_t row_offs
         attr_set = true;
     }
     match_tensor4x2_kernel<<<grid, X2_THREADS, X2_SMEM, s>>>(reinterpret_cast<const uint4 *>(rows), n_rows, exp, units,
-                                                             (uint32_t)q, lo_min_, hi_min_, sink);
+                                                             (uint32_t)q, lo_min_, hi_min_, sink, cand);
+    YPDQ_LAUNCH_CHECK();
+    verify_candidates_kernel<<<(unsigned)n_regions, 128, 0, s>>>(reinterpret_cast<const uint4 *>(rows), cand, sink);
     YPDQ_LAUNCH_CHECK();
     YPDQ_CUDA_TRY(cudaFreeAsync(exp, s));
     return 0;
