@@ -10,4 +10,4 @@ run() { timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node 
 run --steps 10 --warmup 3 > $OUT/bench_${N}gpu.json 2> $OUT/bench_${N}gpu.err; echo "bench N=$N exit $?"; cat $OUT/bench_${N}gpu.json
 run --steps 5 --warmup 3 --db-rows 1000000000 --frames $((1024 / N)) --no-e2e > $OUT/bench_${N}gpu_1b.json 2> $OUT/bench_${N}gpu_1b.err; echo "config5 exit $?"; cat $OUT/bench_${N}gpu_1b.json
 timeout 300 python -m pytest tests/test_gpu_sharded.py -x -q > $OUT/pytest_sharded.log 2>&1; tail -3 $OUT/pytest_sharded.log
-tail -5 $OUT/*.err
+for f in $OUT/*.err; do tail -n 3 $f; done; true
