@@ -156,7 +156,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_gpus):
@@ -209,8 +209,26 @@ def cpu_baseline_leg(args):
 
 
 # --------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
-    global DB_ROWS, FRAMES_PER_GPU
+    global DB_ROWS, FRAMES_PER_GPU, _REAL_STDOUT
+    # Libraries write banners to stdout (NCCL prints "NCCL version ..." at the first collective): keep fd 1 for the
+    # JSON line alone and send everything else to stderr.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -519,7 +537,7 @@ def main():
             "cpu_baseline": cpu_bl,
         }
         line.update(line_extra)
-        print(json.dumps(line), flush=True)
+        emit(line)
     db.close()
     if n_gpus > 1:
         dist.barrier()
