@@ -61,20 +61,14 @@ constexpr uint32_t X2_SBO = 8 * X2_ROW_BYTES;  // row tiles: bytes between 8-row
 constexpr uint32_t X2_LBO = 128;               // bytes between K-adjacent 16-byte chunks
 // needle tile: per 8-needle group six 128-byte chunk blocks [c0', c1, c0, c1, c2, c3]; c0' = chunk 0 with the bias
 // constants, used by the high field; every MMA reads two adjacent blocks
-#ifdef X2_EXPERIMENT_PLAIN_A
-#define X2_A_CHUNKS_CFG 4
-#define X2_EXPERIMENT_NO_FLAGS
-#endif
-#ifndef X2_A_CHUNKS_CFG
-#define X2_A_CHUNKS_CFG 6
-#endif
-constexpr uint32_t X2_A_SBO = X2_A_CHUNKS_CFG * 128;
+constexpr uint32_t X2_A_SBO = 6 * 128;
 constexpr int X2_A_BYTES = (X2_M / 8) * X2_A_SBO;     // 12 KB
 constexpr int X2_A_STAGES = 4;
 #ifndef X2_EPI_WARPS_CFG
 #define X2_EPI_WARPS_CFG 12
 #endif
-constexpr int X2_EPI_WARPS = X2_EPI_WARPS_CFG;   // accumulator columns per warp: 8 -> 120, 12 -> 80, 16 -> 60 (measured: 29.2 / 29.9 / 28.2e12 pairs/s)
+// accumulator columns per epilogue warp: 8 warps -> 120, 12 -> 80, 16 -> 60 (measured: 29.2 / 29.9 / 28.2e12 pairs/s)
+constexpr int X2_EPI_WARPS = X2_EPI_WARPS_CFG;
 constexpr int X2_EXP_THREADS = 64;
 constexpr int X2_WARP_PRODUCER = X2_EPI_WARPS + 2, X2_WARP_MMA = X2_EPI_WARPS + 3;
 constexpr int X2_THREADS = 64 + X2_EXP_THREADS + 32 * X2_EPI_WARPS;
@@ -82,12 +76,7 @@ constexpr uint32_t X2_SF_B = 480, X2_SF_LO = 488, X2_SF_HI = 496;   // TMEM colu
 constexpr uint32_t X2_BITS_BASE = 0x4B400000u;       // bit pattern of 1.5 * 2^23
 constexpr int X2_BIAS_ELEMS = 6;                     // element positions of the high field that hold constants
 constexpr int X2_HI_BITS = 128 - X2_BIAS_ELEMS;      // hash bits the high field compares
-#ifdef X2_EXPERIMENT_UNIT_BIAS     // developer timing experiment (wrong results): are the MMAs slower on 6.0 x 6.0 products?
-constexpr uint32_t X2_ROW_BIAS = 0x00222222u, X2_NEEDLE_BIAS = 0x00222222u;
-#define X2_EXPERIMENT_NO_FLAGS
-#else
 constexpr uint32_t X2_ROW_BIAS = 0x00777777u, X2_NEEDLE_BIAS = 0x00477777u;   // e2m1 6.0 = 0x7, 2.0 = 0x4
-#endif
 constexpr size_t X2_SMEM = 2 * (size_t)X2_SB_BYTES + X2_A_STAGES * (size_t)X2_A_BYTES + 256;
 constexpr int X2_MIN_CHUNK_TILES = 32;               // needle tiles per work unit, at least (amortises the row expansion)
 
@@ -115,13 +104,6 @@ expand_needles_x2_kernel(const uint4 *__restrict__ needles, uint32_t q, uint8_t 
     uint8_t *grp = out + (size_t)(j / X2_M) * X2_A_BYTES + (r >> 3) * X2_A_SBO + (r & 7u) * 16u;
     uint4 c0 = expand32(v.x);
     const uint4 c1 = expand32(v.y);
-#ifdef X2_EXPERIMENT_PLAIN_A
-    *reinterpret_cast<uint4 *>(grp) = c0;
-    *reinterpret_cast<uint4 *>(grp + 128) = c1;
-    *reinterpret_cast<uint4 *>(grp + 256) = expand32(v.z);
-    *reinterpret_cast<uint4 *>(grp + 384) = expand32(v.w);
-    return;
-#endif
     *reinterpret_cast<uint4 *>(grp + 256) = c0;
     c0.x = (c0.x & 0xFF000000u) | X2_NEEDLE_BIAS;
     *reinterpret_cast<uint4 *>(grp) = c0;
@@ -406,12 +388,8 @@ match_tensor4x2_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const ui
                     bar_wait(&a_full[s], (ia / X2_A_STAGES) & 1u);
                     const uint32_t a_addr = s32(sA + (size_t)s * X2_A_BYTES);
                     // needle operand: high field k = 0 reads [c0', c1], low field k = 0 [c0, c1], k = 1 [c2, c3]
-#ifdef X2_EXPERIMENT_PLAIN_A     // developer timing experiment (wrong results): 4-chunk needle groups as without the bias
-                    const uint64_t a_hi0 = x2_desc(a_addr, 128, 512), a_lo0 = a_hi0, a_k1 = x2_desc(a_addr + 256, 128, 512);
-#else
                     const uint64_t a_hi0 = x2_desc(a_addr, 128, X2_A_SBO), a_lo0 = x2_desc(a_addr + 256, 128, X2_A_SBO);
                     const uint64_t a_k1 = x2_desc(a_addr + 512, 128, X2_A_SBO);
-#endif
 #pragma unroll
                     for (uint32_t t = 0; t < X2_STAGES; t++) {
                         bar_wait(&d_empty[t], (ia & 1u) ^ 1u);
@@ -529,18 +507,13 @@ int launch_match_tensor4x2(const uint8_t *rows, size_t n_rows, uint64_t row_offs
     // in the window the high half reads 0x4B40 + dot_hi (- 1 on a borrow); from dot_hi = 64 on the exponent of Z
     // moves and the half reads 0x4B80 + (dot_hi - 64) / 2 (and the low half dot_lo / 2): flag all of those
     const int32_t hi_min = (int32_t)(std::min<uint32_t>((X2_BITS_BASE >> 16) + (uint32_t)hi_dot_min - 1u, 0x4B80u) << 16);
-#if defined(X2_EXPERIMENT_PLAIN_A) || defined(X2_EXPERIMENT_NO_FLAGS)
-    const int32_t lo_min_ = 40000, hi_min_ = 0x7FFF0000;     // nothing is ever flagged: timing only
-#else
-    const int32_t lo_min_ = lo_min, hi_min_ = hi_min;
-#endif
     static bool attr_set = false;
     if (!attr_set) {
         YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor4x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X2_SMEM));
         attr_set = true;
     }
     match_tensor4x2_kernel<<<grid, X2_THREADS, X2_SMEM, s>>>(reinterpret_cast<const uint4 *>(rows), n_rows, exp, units,
-                                                             (uint32_t)q, lo_min_, hi_min_, sink, cand);
+                                                             (uint32_t)q, lo_min, hi_min, sink, cand);
     YPDQ_LAUNCH_CHECK();
     verify_candidates_kernel<<<(unsigned)n_regions, 128, 0, s>>>(reinterpret_cast<const uint4 *>(rows), cand, sink);
     YPDQ_LAUNCH_CHECK();
