@@ -119,6 +119,27 @@ def main():
             print(f"[{tag}] match 10M x  32768 paired thr={thr}: median {med / 1e3:9.2f} ms  {n * 32768 / med / 1e6:8.3f} Tpairs/s")
             cnt.zero_()
         db.close()
+    if "cross" in what:   # crossover between the tiled POPC kernel and the paired tensor kernel
+        n = (10_000_000 // 2048 + 1) * 2048
+        db = yp.CudaVectorDatabase(synthetic_rows=n)
+        m = yp.CudaMatcher(db, 31)
+        out = torch.zeros((1 << 20, 16), dtype=torch.uint8, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        small = yp.CudaVectorDatabase(synthetic_rows=1_000_000)
+        ms = yp.CudaMatcher(small, 31)
+        for q in (128, 1024):
+            needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
+            med, best = timeit(lambda: ms.find_device(needles, q, out, 1 << 20, cnt, algo=yp.ALGO_TENSOR_PAIRED), iters=10, warm=2)
+            print(f"cross 1M x {q:4d} paired: median {med:9.1f} us")
+            cnt.zero_()
+        small.close()
+        for q in (8, 16, 32, 64, 128, 256, 512):
+            needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
+            for name, algo in (("tiled", yp.ALGO_TILED), ("paired", yp.ALGO_TENSOR_PAIRED)):
+                med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 20, cnt, algo=algo), iters=10, warm=2)
+                print(f"cross 10M x {q:4d} {name:6s}: median {med:9.1f} us  {n * q / med / 1e6:8.3f} Tpairs/s")
+                cnt.zero_()
+        db.close()
     if "hashpx" in what:   # hash kernel per pixel format
         k = yp.CudaKernel(0)
         n = 4096

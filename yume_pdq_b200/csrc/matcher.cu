@@ -425,11 +425,13 @@ int launch_match(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const 
     const uint4 *rows4 = reinterpret_cast<const uint4 *>(rows);
     const uint4 *needles4 = reinterpret_cast<const uint4 *>(needles);
     if (algo == YUME_PDQ_CUDA_ALGO_AUTO) {
-        // Measured on B200 (10M rows): 8 needles tiled 58 us / stream 80 us / exact 157 us; 1024 needles
-        // tensor 3.8 ms vs tiled 4.7 ms; 128 needles tiled 0.60 ms vs tensor 0.69 ms.  The tensor-core
-        // kernels amortise one row-tile expansion over q / 128 needle tiles, so they win for large batches;
+        // Measured on B200 (10M rows, threshold 31; profiles/r01ag): tiled POPC kernel 54 us for 8 needles, 86 us for
+        // 16, 156 us for 32, 302 us for 64 (2.1e12 pairs/s from there on); paired tensor kernel ~170 us for anything up
+        // to 128 needles (one needle tile: the row expansion is the floor), 190 us for 256, 254 us for 512, 0.45 ms for
+        // 1024.  Above threshold 36 the tensor path is the unpaired full kernel (1024 needles 0.8 ms vs tiled 4.7 ms);
         // the 96-bit prefix bound of the POPC kernels stops filtering once threshold approaches 48.
-        if (q >= 512)
+        // (a persistent tensor launch costs ~20 us before the first row: not for tiny shards)
+        if (q >= (threshold <= 36 ? 48u : 512u) && (q >= 512 || n_rows >= 100000))
             algo = YUME_PDQ_CUDA_ALGO_TENSOR;
         else if (threshold > 40)
             algo = YUME_PDQ_CUDA_ALGO_EXACT;

@@ -64,14 +64,28 @@ constexpr uint32_t X2_LBO = 128;               // bytes between K-adjacent 16-by
 constexpr uint32_t X2_A_SBO = 6 * 128;
 constexpr int X2_A_BYTES = (X2_M / 8) * X2_A_SBO;     // 12 KB
 constexpr int X2_A_STAGES = 4;
-#ifndef X2_EPI_WARPS_CFG
-#define X2_EPI_WARPS_CFG 12
-#endif
-// accumulator columns per epilogue warp: 8 warps -> 120, 12 -> 80, 16 -> 60 (measured: 29.2 / 29.9 / 28.2e12 pairs/s)
-constexpr int X2_EPI_WARPS = X2_EPI_WARPS_CFG;
-constexpr int X2_EXP_THREADS = 64;
-constexpr int X2_WARP_PRODUCER = X2_EPI_WARPS + 2, X2_WARP_MMA = X2_EPI_WARPS + 3;
-constexpr int X2_THREADS = 64 + X2_EXP_THREADS + 32 * X2_EPI_WARPS;
+// Warp roles.  Two configurations of the same kernel:
+//  * X2Large (12 epilogue warps x 80 columns, 2 expander warps; 16 warps x 128 registers): many needle tiles per
+//    unit, the epilogue is the bottleneck (8 / 12 / 16 epilogue warps: 29.2 / 29.9 / 28.2e12 pairs/s);
+//  * X2Small (8 epilogue warps x 120 columns, 6 expander warps; 16 warps): few needle tiles per unit, expanding the
+//    960 rows of a super-tile is the bottleneck (two expander warps need ~11,000 clk for it, the MMAs of one needle
+//    tile 960).  The register file is re-split at run time (setmaxnreg): 176 per epilogue thread, 80 for the rest.
+// Warps [0, EPI) are epilogue warps (whole warpgroups); of the following warps two are the needle producer and the
+// MMA issuer, the others expand rows.
+template <int EPI, int EXP>
+struct X2Cfg {
+    static_assert(EPI % 4 == 0 && (EXP + 2) % 4 == 0, "whole warpgroups per role class");
+    static constexpr int EPI_WARPS = EPI, EXP_WARPS = EXP, EXP_THREADS = 32 * EXP;
+    static constexpr int WARP_PRODUCER = EPI + (EXP > 2 ? 4 : 2), WARP_MMA = WARP_PRODUCER + 1;
+    static constexpr int THREADS = 32 * (EPI + EXP + 2);
+    static constexpr int EB = 240 / (EPI / 4);            // accumulator columns per epilogue warp
+    static constexpr bool SPLIT_REGS = EXP > 2;
+    static constexpr int REGS_EPI = 176, REGS_OTHER = 80;
+    static_assert(!SPLIT_REGS || 32 * (EPI * REGS_EPI + (EXP + 2) * REGS_OTHER) <= 65536 / THREADS / 8 * 8 * THREADS, "register pool");
+};
+using X2Large = X2Cfg<12, 2>;
+using X2Small = X2Cfg<8, 6>;
+constexpr uint32_t X2_SMALL_MAX_TILES = 16;    // needle tiles (of 128) up to which X2Small is used
 constexpr uint32_t X2_SF_B = 480, X2_SF_LO = 488, X2_SF_HI = 496;   // TMEM columns of the scale-factor regions
 constexpr uint32_t X2_BITS_BASE = 0x4B400000u;       // bit pattern of 1.5 * 2^23
 constexpr int X2_BIAS_ELEMS = 6;                     // element positions of the high field that hold constants
@@ -80,7 +94,6 @@ constexpr uint32_t X2_ROW_BIAS = 0x00777777u, X2_NEEDLE_BIAS = 0x00477777u;   //
 constexpr size_t X2_SMEM = 2 * (size_t)X2_SB_BYTES + X2_A_STAGES * (size_t)X2_A_BYTES + 256;
 constexpr int X2_MIN_CHUNK_TILES = 32;               // needle tiles per work unit, at least (amortises the row expansion)
 
-constexpr int X2_EB = X2_N / (X2_EPI_WARPS / 4);   // accumulator columns per epilogue warp
 // block-scaled instruction descriptor: A = B = e2m1, both K-major, ue8m0 scales, dense K = 64
 constexpr uint32_t X2_IDESC = (1u << 7) | (1u << 10) | ((uint32_t)(X2_N >> 3) << 17) | (1u << 23) | ((uint32_t)(X2_M >> 4) << 24);
 
@@ -254,18 +267,19 @@ struct X2Cursor {
     __device__ __forceinline__ uint32_t m1(const X2Units &u) const { return min(u.n_mtiles, (ch + 1) * u.chunk_tiles); }
 };
 
-// Epilogue of one warp: TMEM lanes 32 quad .. 32 quad + 31 (needles), columns X2_EB part .. X2_EB part + X2_EB - 1 of
-// both stages
+// Epilogue of one warp: TMEM lanes 32 quad .. 32 quad + 31 (needles), columns EB part .. EB part + EB - 1 of both stages
+template <class Cfg>
 __device__ __forceinline__ void x2_epilogue(uint32_t tmem, uint32_t quad, uint32_t part, uint32_t lane, uint64_t *d_full,
                                             uint64_t *d_empty, const X2Units &units, uint32_t q, int32_t lo_min, int32_t hi_min,
                                             uint64_t n_rows, const uint4 *__restrict__ rows, const Tc4Sink &sink,
                                             const X2CandList &cand)
 {
+    constexpr int X2_EB = Cfg::EB;
     uint32_t dfull = s32(&d_full[0]), dempty = s32(&d_empty[0]);
     uint32_t tbase = tmem + ((quad * 32u) << 16) + part * X2_EB;
     int32_t lmin = lo_min, hmin = hi_min;
     asm volatile("" : "+r"(dfull), "+r"(dempty), "+r"(tbase), "+r"(lmin), "+r"(hmin));   // keep them in registers
-    const uint32_t region_id = blockIdx.x * X2_EPI_WARPS + part * 4 + quad;
+    const uint32_t region_id = blockIdx.x * Cfg::EPI_WARPS + part * 4 + quad;
     X2Candidate *region = cand.items + (size_t)region_id * X2_CAND_SLOTS;
     uint32_t n_cand = 0;
     int32_t v[X2_EB];
@@ -300,7 +314,8 @@ __device__ __forceinline__ void x2_epilogue(uint32_t tmem, uint32_t quad, uint32
         cand.counts[region_id] = n_cand;
 }
 
-__global__ void __launch_bounds__(X2_THREADS, 1)
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
 match_tensor4x2_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint8_t *__restrict__ needles_exp,
                        X2Units units, uint32_t q, int32_t lo_min, int32_t hi_min, Tc4Sink sink, X2CandList cand)
 {
@@ -319,16 +334,16 @@ match_tensor4x2_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const ui
             bar_init(&a_empty[i], 1);
         }
         for (int i = 0; i < 2; i++) {
-            bar_init(&b_full[i], X2_EXP_THREADS);
+            bar_init(&b_full[i], Cfg::EXP_THREADS);
             bar_init(&b_empty[i], 1);
         }
         for (int i = 0; i < X2_STAGES; i++) {
             bar_init(&d_full[i], 1);
-            bar_init(&d_empty[i], X2_EPI_WARPS);
+            bar_init(&d_empty[i], Cfg::EPI_WARPS);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == X2_WARP_MMA) {
+    if (warp == Cfg::WARP_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(512));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -350,8 +365,10 @@ match_tensor4x2_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const ui
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    if (warp == X2_WARP_PRODUCER) {
+    if (warp == Cfg::WARP_PRODUCER) {
         // ===== needle tile producer =====
+        if constexpr (Cfg::SPLIT_REGS)
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_OTHER));
         if (lane == 0) {
             uint32_t it = 0;
             for (X2Cursor c(units); c.valid(units); c.next(units)) {
@@ -364,8 +381,10 @@ match_tensor4x2_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const ui
                 }
             }
         }
-    } else if (warp == X2_WARP_MMA) {
+    } else if (warp == Cfg::WARP_MMA) {
         // ===== MMA issuer: 4 MMAs per (needle tile, accumulator stage) =====
+        if constexpr (Cfg::SPLIT_REGS)
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_OTHER));
         if (lane == 0) {
             const uint32_t sf_b = tmem + X2_SF_B, sf_lo = tmem + X2_SF_LO, sf_hi = tmem + X2_SF_HI;
             auto mma = [&](uint32_t d_addr, uint64_t da, uint64_t db, uint32_t idesc, uint32_t sfa, uint32_t accumulate) {
@@ -409,25 +428,42 @@ match_tensor4x2_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const ui
                 umma_commit(&b_empty[b]);             // row buffer may be overwritten
             }
         }
-    } else if (warp >= X2_EPI_WARPS) {
-        // ===== row expanders: 64 threads, thread t expands rows t, t+64, ... of the super-tile =====
-        const uint32_t t = threadIdx.x - 32 * X2_EPI_WARPS;
-        uint32_t i = 0;
-        for (X2Cursor c(units); c.valid(units); c.next(units), i++) {
-            const uint64_t st = c.st;
-            const uint32_t b = i & 1u;
-            uint8_t *buf = sB + (size_t)b * X2_SB_BYTES;
-            // all of the thread's rows are requested before the first one is used: with one HBM round trip per group
-            // of four the expansion of a super-tile took longer than the MMAs of an 8-needle-tile unit (q = 1024)
-            constexpr uint32_t PER_THREAD = (X2_ROWS + X2_EXP_THREADS - 1) / X2_EXP_THREADS;     // 15
-            uint4 lo[PER_THREAD];
+    } else if (warp >= Cfg::EPI_WARPS) {
+        // ===== row expanders: thread t expands rows t, t + EXP_THREADS, ... of the super-tile =====
+        if constexpr (Cfg::SPLIT_REGS)
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_OTHER));
+        constexpr uint32_t X2_EXP_THREADS = Cfg::EXP_THREADS;
+        const uint32_t t = (uint32_t)(warp < Cfg::WARP_PRODUCER ? warp - Cfg::EPI_WARPS : warp - Cfg::EPI_WARPS - 2) * 32u + (uint32_t)lane;
+        // All of the thread's rows are requested before the first one is used (one HBM round trip per super-tile),
+        // and with few rows per thread (X2Small) the rows of the NEXT unit are requested before this unit's are
+        // expanded, so the round trip overlaps the expansion.
+        constexpr uint32_t PER_THREAD = (X2_ROWS + X2_EXP_THREADS - 1) / X2_EXP_THREADS;     // 15 or 5
+        constexpr bool PREFETCH = PER_THREAD <= 5;
+        auto request = [&](uint4 (&dst)[PER_THREAD], uint64_t st) {
 #pragma unroll
             for (uint32_t h = 0; h < PER_THREAD; h++) {
                 const uint32_t r = t + X2_EXP_THREADS * h;
                 const uint64_t row = st * X2_ROWS + r;
-                lo[h] = make_uint4(0, 0, 0, 0);
+                dst[h] = make_uint4(0, 0, 0, 0);
                 if (r < X2_ROWS && row < n_rows)
-                    lo[h] = __ldg(rows + 2 * row);
+                    dst[h] = __ldg(rows + 2 * row);
+            }
+        };
+        uint4 lo[PER_THREAD], nxt[PREFETCH ? PER_THREAD : 1];
+        uint32_t i = 0;
+        X2Cursor c(units);
+        if (PREFETCH && c.valid(units))
+            request(lo, c.st);
+        while (c.valid(units)) {
+            const uint32_t b = i & 1u;
+            uint8_t *buf = sB + (size_t)b * X2_SB_BYTES;
+            if constexpr (PREFETCH) {
+                X2Cursor c2 = c;
+                c2.next(units);
+                if (c2.valid(units))
+                    request(reinterpret_cast<uint4(&)[PER_THREAD]>(nxt), c2.st);
+            } else {
+                request(lo, c.st);
             }
             bar_wait(&b_empty[b], ((i >> 1) & 1u) ^ 1u);
 #pragma unroll
@@ -449,17 +485,26 @@ match_tensor4x2_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const ui
                     *reinterpret_cast<uint4 *>(p + 3 * X2_LBO) = expand32(lo[h].w);
                 }
             }
+            if constexpr (PREFETCH) {
+#pragma unroll
+                for (uint32_t h = 0; h < PER_THREAD; h++)
+                    lo[h] = nxt[h];
+            }
+            c.next(units);
+            i++;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
             bar_arrive(&b_full[b]);
         }
     } else {
-        x2_epilogue(tmem, (uint32_t)warp & 3u, (uint32_t)warp >> 2, (uint32_t)lane, d_full, d_empty, units, q, lo_min, hi_min,
+        if constexpr (Cfg::SPLIT_REGS)
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_EPI));
+        x2_epilogue<Cfg>(tmem, (uint32_t)warp & 3u, (uint32_t)warp >> 2, (uint32_t)lane, d_full, d_empty, units, q, lo_min, hi_min,
                     n_rows, rows, sink, cand);
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == X2_WARP_MMA)
+    if (warp == Cfg::WARP_MMA)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
@@ -490,7 +535,8 @@ int launch_match_tensor4x2(const uint8_t *rows, size_t n_rows, uint64_t row_offs
     const unsigned grid = (unsigned)std::min<uint64_t>(units.n_stiles * units.n_chunks, (uint64_t)sm_count);
     // one stream-ordered scratch block: expanded needle tiles | candidate counts | candidate regions
     const size_t exp_bytes = (size_t)n_mtiles * X2_A_BYTES;
-    const size_t n_regions = (size_t)grid * X2_EPI_WARPS, count_bytes = (n_regions * 4 + 255) / 256 * 256;
+    const bool small = n_mtiles <= X2_SMALL_MAX_TILES;
+    const size_t n_regions = (size_t)grid * (small ? X2Small::EPI_WARPS : X2Large::EPI_WARPS), count_bytes = (n_regions * 4 + 255) / 256 * 256;
     uint8_t *exp = nullptr;
     cudaError_t e = cudaMallocAsync(&exp, exp_bytes + count_bytes + n_regions * X2_CAND_SLOTS * sizeof(X2Candidate), s);
     if (e != cudaSuccess) {
@@ -507,15 +553,23 @@ int launch_match_tensor4x2(const uint8_t *rows, size_t n_rows, uint64_t row_offs
     // in the window the high half reads 0x4B40 + dot_hi (- 1 on a borrow); from dot_hi = 64 on the exponent of Z
     // moves and the half reads 0x4B80 + (dot_hi - 64) / 2 (and the low half dot_lo / 2): flag all of those
     const int32_t hi_min = (int32_t)(std::min<uint32_t>((X2_BITS_BASE >> 16) + (uint32_t)hi_dot_min - 1u, 0x4B80u) << 16);
+    const uint4 *rows4 = reinterpret_cast<const uint4 *>(rows);
     static bool attr_set = false;
     if (!attr_set) {
-        YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor4x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)X2_SMEM));
+        YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor4x2_kernel<X2Large>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)X2_SMEM));
+        YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor4x2_kernel<X2Small>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)X2_SMEM));
         attr_set = true;
     }
-    match_tensor4x2_kernel<<<grid, X2_THREADS, X2_SMEM, s>>>(reinterpret_cast<const uint4 *>(rows), n_rows, exp, units,
-                                                             (uint32_t)q, lo_min, hi_min, sink, cand);
+    if (small)
+        match_tensor4x2_kernel<X2Small><<<grid, X2Small::THREADS, X2_SMEM, s>>>(rows4, n_rows, exp, units, (uint32_t)q, lo_min,
+                                                                                hi_min, sink, cand);
+    else
+        match_tensor4x2_kernel<X2Large><<<grid, X2Large::THREADS, X2_SMEM, s>>>(rows4, n_rows, exp, units, (uint32_t)q, lo_min,
+                                                                                hi_min, sink, cand);
     YPDQ_LAUNCH_CHECK();
-    verify_candidates_kernel<<<(unsigned)n_regions, 128, 0, s>>>(reinterpret_cast<const uint4 *>(rows), cand, sink);
+    verify_candidates_kernel<<<(unsigned)n_regions, 128, 0, s>>>(rows4, cand, sink);
     YPDQ_LAUNCH_CHECK();
     YPDQ_CUDA_TRY(cudaFreeAsync(exp, s));
     return 0;

@@ -68,13 +68,16 @@ __device__ __forceinline__ void umma_commit(uint64_t *b)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(b)) : "memory");
 }
 
-// 8 bits -> 8 e2m1 nibbles: bit i -> nibble i; bit 1 -> 0x2 (+1.0), bit 0 -> 0xA (-1.0)
+// 8 bits -> 8 e2m1 nibbles: bit i -> nibble i; bit 1 -> 0x2 (+1.0), bit 0 -> 0xA (-1.0).  The spreading steps
+// (x | x << k) are written as multiplications (the shifted copies never overlap), so they issue on the FMA pipe
+// (IMAD) and only the three masks load the ALU pipe; the last step folds shift and sign into one multiply-add:
+// nibble = 0xA - 8 * bit.
 __device__ __forceinline__ uint32_t expand8(uint32_t x)
 {
-    x = (x | (x << 12)) & 0x000F000Fu;
-    x = (x | (x << 6)) & 0x03030303u;
-    x = (x | (x << 3)) & 0x11111111u;
-    return (x << 3) ^ 0xAAAAAAAAu;
+    x = (x * 0x1001u) & 0x000F000Fu;
+    x = (x * 0x41u) & 0x03030303u;
+    x = (x * 0x9u) & 0x11111111u;
+    return 0xAAAAAAAAu - 8u * x;
 }
 // one 32-bit hash word -> one 16-byte K chunk (32 e2m1 elements)
 __device__ __forceinline__ uint4 expand32(uint32_t w)
