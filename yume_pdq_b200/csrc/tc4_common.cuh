@@ -22,15 +22,21 @@ __device__ __forceinline__ void bar_expect_tx(uint64_t *b, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
 }
+#ifndef T4_SUSPEND_NS_CFG
+#define T4_SUSPEND_NS_CFG 2000
+#endif
+// suspend-time hint of mbarrier.try_wait: a waiting warp is parked for up to this long (it wakes as soon as the
+// phase completes) instead of re-issuing the poll, which costs the working warps of its scheduler issue slots
+constexpr uint32_t T4_SUSPEND_NS = T4_SUSPEND_NS_CFG;
 __device__ __forceinline__ bool bar_try(uint64_t *b, uint32_t parity)
 {
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(s32(b)), "r"(parity)
+        : "r"(s32(b)), "r"(parity), "r"(T4_SUSPEND_NS)
         : "memory");
     return done != 0;
 }
@@ -46,11 +52,11 @@ __device__ __forceinline__ void bar_wait_addr(uint32_t addr, uint32_t parity)
     asm volatile(
         "{\n\t.reg .pred p;\n"
         "T4_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra T4_DONE;\n\t"
         "bra T4_WAIT;\n"
         "T4_DONE:\n\t}" ::"r"(addr),
-        "r"(parity)
+        "r"(parity), "r"(T4_SUSPEND_NS)
         : "memory");
 }
 __device__ __forceinline__ void bar_arrive_addr(uint32_t addr)
