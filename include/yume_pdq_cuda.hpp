@@ -78,6 +78,15 @@ public:
     void hash_batch(const float *frames, size_t n, uint8_t *hashes, float *quality = nullptr,
                     float *thresholds = nullptr, float *pdqf = nullptr) const
     { check(yume_pdq_cuda_hash_batch(device_, frames, n, hashes, quality, thresholds, pdqf, stream_), "hash_batch"); }
+    // the same for raw 8-bit frames (YUME_PDQ_CUDA_PIXEL_LUMA8 / RGB8 / RGBA8): the CLI's input conversion
+    // (main.rs:486-608, Kernel::cvt_rgb8_to_luma8f mod.rs:303-340) fused into the hash kernel
+    void hash_batch_pixels(const void *frames, int pixel_format, size_t n, uint8_t *hashes, float *quality = nullptr,
+                           float *thresholds = nullptr, float *pdqf = nullptr) const
+    { check(yume_pdq_cuda_hash_batch_pixels(device_, frames, pixel_format, n, hashes, quality, thresholds, pdqf, stream_),
+            "hash_batch_pixels"); }
+    // Kernel::cvt_rgb8_to_luma8f / cvt_rgba8_to_luma8f on their own (coeff = {R, G, B}, nullptr = ITU table)
+    void cvt_to_luma8f(const void *pixels, int pixel_format, size_t n_pixels, float *out, const float *coeff = nullptr) const
+    { check(yume_pdq_cuda_cvt_to_luma8f(device_, pixels, pixel_format, n_pixels, coeff, out, stream_), "cvt_to_luma8f"); }
     void dihedrals_batch(const float *pdqf, const float *thr0, size_t n, uint8_t *hashes, float *quality,
                          float *thresholds) const
     { check(yume_pdq_cuda_dihedrals_batch(device_, pdqf, thr0, n, hashes, quality, thresholds, stream_), "dihedrals_batch"); }
@@ -146,6 +155,22 @@ public:
             if (rc == YUME_PDQ_CUDA_E_CAPACITY) { cap = n; continue; }
             check(rc, "find");
             out.resize(n);
+            return out;
+        }
+    }
+    // hash + 8 dihedrals + match for a batch of frames (examples/end_to_end.rs:224-256 in one pipelined call);
+    // needle index of a match = 8 * frame + dihedral
+    std::vector<YumePDQ_Match> screen(const void *frames, int pixel_format, size_t n, uint8_t *hashes = nullptr,
+                                      float *quality = nullptr, size_t cap = 1 << 16) const
+    {
+        for (;;) {
+            std::vector<YumePDQ_Match> out(cap);
+            size_t found = 0;
+            int rc = yume_pdq_cuda_screen_batch_pixels(db_, frames, pixel_format, n, threshold_, hashes, quality, out.data(),
+                                                       cap, &found, stream_);
+            if (rc == YUME_PDQ_CUDA_E_CAPACITY) { cap = found; continue; }
+            check(rc, "screen");
+            out.resize(found);
             return out;
         }
     }

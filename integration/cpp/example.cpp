@@ -37,6 +37,24 @@ int main()
             return 1;
         }
         std::printf("found at row %zu, needle %zu (%s)\n", found->first, found->second, ypdq::CudaMatcher::ident());
+
+        // the same frame as raw 8-bit luma (what `yume-pdq pipe` ingests): conversion fused into the hasher, and
+        // hash + dihedrals + match in one call
+        std::vector<uint8_t> luma(512 * 512);
+        for (size_t i = 0; i < luma.size(); i++)
+            luma[i] = uint8_t(frame[i]);
+        std::vector<uint8_t> hashes8(8 * 32);
+        kernel.hash_batch_pixels(luma.data(), YUME_PDQ_CUDA_PIXEL_LUMA8, 1, hashes8.data());
+        if (hashes8 != hashes) {
+            std::printf("FAILED: luma8 and f32 hashes differ\n");
+            return 1;
+        }
+        auto matches = matcher.screen(luma.data(), YUME_PDQ_CUDA_PIXEL_LUMA8, 1);
+        if (matches.size() != 1 || matches[0].row != 123456 || matches[0].needle != 5 || matches[0].dist != 4) {
+            std::printf("FAILED: screen() returned %zu matches\n", matches.size());
+            return 1;
+        }
+        std::printf("screen: row %llu needle %u dist %u\n", (unsigned long long)matches[0].row, matches[0].needle, matches[0].dist);
         return 0;
     } catch (const ypdq::Error &e) {
         std::printf("error: %s\n", e.what());
