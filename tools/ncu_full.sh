@@ -8,6 +8,7 @@ for what in "$@"; do
     hash)   K=hash_fused_kernel ;;
     scan)   K=match_tiled_kernel ;;
     tensor) K=match_tensor4 ;;
+    tensor128) K=match_tensor4x2 ;;
     *)      K=$what ;;
   esac
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 2 -c 1 -f -o $OUT/ncu_$what \
