@@ -39,7 +39,14 @@ namespace {
 
 constexpr int HT = 128;          // threads per CTA
 constexpr int TSTRIDE = 129;     // padded row stride of the 16x127 stage-1 result
-constexpr int PREFETCH_AHEAD = 8;
+// L2 prefetch distance in tent rows (4 input rows = 8 KB of f32 each).  Measured on a B200, 4096 f32 frames:
+// 2 -> 696 us, 3 -> 707, 4 -> 673, 5 -> 668, 6 -> 660 (6.50 TB/s), 7 -> 679, 8 -> 756, 16 -> 928, 32 -> 1168: beyond
+// 6 windows x 592 resident CTAs the prefetched lines start to be evicted from L2 before they are used (ncu at 8:
+// DRAM reads 1.22 x the frame bytes).
+#ifndef HASH_PREFETCH_AHEAD_CFG
+#define HASH_PREFETCH_AHEAD_CFG 6
+#endif
+constexpr int PREFETCH_AHEAD = HASH_PREFETCH_AHEAD_CFG;
 
 __device__ __align__(16) float g_dt[127 * 16];          // D transposed, g_dt[k2*16 + k] = D[k][k2]
 __constant__ uint32_t c_tent_bits[49];    // W[di][dj], read as constant-bank operands
