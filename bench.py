@@ -380,6 +380,12 @@ def main():
         ts = [a.elapsed_time(b) for a, b in ev]
         return float(np.mean(ts)), float(np.median(ts)), float(np.min(ts))
 
+    # DRAM traffic per launch from the ncu captures under profiles/r01ak/ (bytes read + written), per row / per frame;
+    # reported only for the sizes those captures were taken at (one GPU, the default DB, f32 frames)
+    default_sizes = n_gpus == 1 and DB_ROWS == (10_000_000 // 2048 + 1) * 2048
+    traffic_tensor = (324819200 + 3689984) / 10_000_384 * shard_rows if default_sizes and B == 4096 else None
+    traffic_hash = (1235472640 + 4763904) / 1184 * B if default_sizes else None
+    traffic_scan = (320080128 + 5022464) / 10_000_384 * shard_rows if default_sizes else None
     line_extra = {}
     if rank == 0:
         flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
@@ -427,12 +433,14 @@ def main():
             "tensor_ops_per_pair": ops_per_pair, "executed_tensor_ops_per_pair": executed_per_pair,
             "executed_frac": pairs * executed_per_pair / (m_mean * 1e-3) / 1e12 / mxf4_peak,
             "tpairs_per_s": pairs / (m_mean * 1e-3) / 1e12,
-            "traffic": None, "ms_per_launch": m_mean, "share_of_step": share,
+            "traffic": traffic_tensor, "traffic_source": "profiles/r01ak/traffic_tensor32k.csv (ncu, same sizes)",
+            "ms_per_launch": m_mean, "share_of_step": share,
         }
         line_extra["roofline_hash"] = {
             "kernel": "hash_fused_kernel", "bound": "hbm", "achieved": hash_bytes / (h_mean * 1e-3) / 1e9,
             "peak": hbm_peak, "unit": "GB/s", "frac": hash_bytes / (h_mean * 1e-3) / 1e9 / hbm_peak,
-            "peak_source": peak_src, "traffic": None, "ms_per_launch": h_mean,
+            "peak_source": peak_src, "traffic": traffic_hash, "algorithmic_bytes": hash_bytes,
+            "traffic_source": "profiles/r01ak/traffic_hash.csv (ncu, scaled per frame)", "ms_per_launch": h_mean,
             "images_per_s": B / (h_mean * 1e-3),
         }
         line_extra["scan"] = {
@@ -440,7 +448,8 @@ def main():
             "us": s_mean * 1e3, "us_median": s_med * 1e3, "us_min": s_min * 1e3,
             "db_gbs": scan_bytes / (s_mean * 1e-3) / 1e9, "bound": "hbm", "peak": hbm_peak,
             "frac": scan_bytes / (s_mean * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src,
-            "rows_per_s": shard_rows / (s_mean * 1e-3), "traffic": None,
+            "rows_per_s": shard_rows / (s_mean * 1e-3), "traffic": traffic_scan, "algorithmic_bytes": scan_bytes,
+            "traffic_source": "profiles/r01ak/traffic_scan.csv (ncu, same sizes)",
         }
         del flush
 

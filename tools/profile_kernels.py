@@ -23,7 +23,7 @@ if "hash" in what:
     for _ in range(3):
         k.hash_batch(frames, out=outs)
     torch.cuda.synchronize()
-if {"scan", "stream", "tiled", "exact", "tensor", "tensor128"} & set(what):
+if {"scan", "stream", "tiled", "exact", "tensor", "tensor128", "tensor32k"} & set(what):
     n = (10_000_000 // 2048 + 1) * 2048
     db = yp.CudaVectorDatabase(synthetic_rows=n)
     m = yp.CudaMatcher(db, 31)
@@ -43,6 +43,10 @@ if {"scan", "stream", "tiled", "exact", "tensor", "tensor128"} & set(what):
             m.find_device(nbig, 2048, out, 1 << 16, cnt, algo=yp.ALGO_TILED)
         if "tensor" in what:
             m.find_device(nbig4, 4096, out, 1 << 16, cnt, algo=yp.ALGO_TENSOR)
+        if "tensor32k" in what:     # the bench's needle batch
+            if "nb32" not in globals():
+                nb32 = torch.from_numpy(rng.integers(0, 256, size=(32768, 32), dtype=np.uint8)).cuda()
+            m.find_device(nb32, 32768, out, 1 << 16, cnt, algo=yp.ALGO_TENSOR)
         if "tensor128" in what:     # one needle tile per unit: the X2Small configuration of the paired kernel
             m.find_device(nbig[:128].contiguous(), 128, out, 1 << 16, cnt, algo=yp.ALGO_TENSOR_PAIRED)
     torch.cuda.synchronize()
