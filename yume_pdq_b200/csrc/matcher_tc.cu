@@ -330,11 +330,8 @@ int launch_match_tensor(const uint8_t *rows, size_t n_rows, uint64_t row_offset,
     expand_needles_kernel<<<(threads + 255) / 256, 256, 0, s>>>(reinterpret_cast<const uint4 *>(needles), (uint32_t)q, exp,
                                                                 n_mtiles);
     YPDQ_LAUNCH_CHECK();
-    static bool attr_set = false;
-    if (!attr_set) {
-        YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
-        attr_set = true;
-    }
+    // per launch: function attributes are per device, and the call costs microseconds
+    YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     TcSink sink{out, cap, count, min_key, row_offset, (uint64_t)q, mode, needle_base};
     const uint64_t n_ntiles = (n_rows + TC_N - 1) / TC_N;
     const unsigned grid = (unsigned)std::min<uint64_t>(n_ntiles, (uint64_t)sm_count);

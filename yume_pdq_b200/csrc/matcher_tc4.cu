@@ -448,12 +448,9 @@ static int launch_tc4(const uint8_t *rows, size_t n_rows, const uint8_t *needles
     const float dot_min = (float)(Cfg::KBITS - 2 * (int32_t)threshold);
     int32_t min_bits;
     memcpy(&min_bits, &dot_min, 4);
-    static bool attr_set = false;
-    if (!attr_set) {
-        YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor4_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)t4_smem<KC>()));
-        attr_set = true;
-    }
+    // per launch: function attributes are per device, and the call costs microseconds
+    YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor4_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)t4_smem<KC>()));
     match_tensor4_kernel<KC><<<grid, T4_THREADS, t4_smem<KC>(), s>>>(reinterpret_cast<const uint4 *>(rows), n_rows, exp,
                                                                      n_mtiles, (uint32_t)q, min_bits, sink);
     YPDQ_LAUNCH_CHECK();

@@ -554,14 +554,11 @@ int launch_match_tensor4x2(const uint8_t *rows, size_t n_rows, uint64_t row_offs
     // moves and the half reads 0x4B80 + (dot_hi - 64) / 2 (and the low half dot_lo / 2): flag all of those
     const int32_t hi_min = (int32_t)(std::min<uint32_t>((X2_BITS_BASE >> 16) + (uint32_t)hi_dot_min - 1u, 0x4B80u) << 16);
     const uint4 *rows4 = reinterpret_cast<const uint4 *>(rows);
-    static bool attr_set = false;
-    if (!attr_set) {
-        YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor4x2_kernel<X2Large>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)X2_SMEM));
-        YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor4x2_kernel<X2Small>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)X2_SMEM));
-        attr_set = true;
-    }
+    // per launch: function attributes are per device, and the call costs microseconds
+    YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor4x2_kernel<X2Large>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)X2_SMEM));
+    YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor4x2_kernel<X2Small>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)X2_SMEM));
     if (small)
         match_tensor4x2_kernel<X2Small><<<grid, X2Small::THREADS, X2_SMEM, s>>>(rows4, n_rows, exp, units, (uint32_t)q, lo_min,
                                                                                 hi_min, sink, cand);
