@@ -107,3 +107,12 @@ def test_rust_fixed_rounding():
     assert rust_fixed(np.float32(2.5), 0) == "2" and rust_fixed(np.float32(3.5), 0) == "4"   # ties to even on exact ties
     assert rust_fixed(np.float32(-0.0), 5) == "-0.00000"
     assert wire_record("q+hex", bytes(32), np.float32(0.999994)) .startswith(b"99.999:")
+
+
+def test_pipe_fails_loudly_without_a_gpu(cli):
+    """No CPU fallback: with a valid format but no usable sm_100 device `pipe` exits 128 and says so."""
+    import yume_pdq_b200 as yp
+    if yp.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    r = subprocess.run([cli, "pipe", "-f", "hex+lf"], input=bytes(512 * 512), capture_output=True, timeout=60)
+    assert r.returncode == 128 and r.stdout == b"" and b"no CPU fallback" in r.stderr
