@@ -74,3 +74,19 @@ def test_product_never_imports_oracle():
                     code = line.split("//")[0].split("#")[0] if not f.endswith(".py") else line.split("#")[0]
                     assert "import oracle" not in code and "from oracle" not in code, (f, line)
                     assert "liboracle" not in code and "libcpu_baseline" not in code, (f, line)
+
+
+def test_header_is_valid_c_and_example_links(tmp_path):
+    """include/yume_pdq_cuda.h must be usable from plain C (the reference's C users include a C header), and the C
+    example of the reference's two-function ABI must link against the library (it needs a GPU to run)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "yume_pdq_b200")
+    exe = tmp_path / "c_example"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "integration", "c", "example.c"), "-L" + lib_dir, "-lyume_pdq_cuda", "-lm",
+                    "-Wl,-rpath," + lib_dir, "-o", str(exe)], check=True, timeout=120)
+    import yume_pdq_b200 as yp
+    if yp.device_count() == 0:      # no CPU fallback: the example reports the missing device and exits 2
+        r = subprocess.run([str(exe)], capture_output=True, timeout=120)
+        assert r.returncode == 2 and b"no CPU fallback" in r.stderr
