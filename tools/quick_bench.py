@@ -107,7 +107,7 @@ def main():
         m = yp.CudaMatcher(db, 31)
         out = torch.zeros((1 << 20, 16), dtype=torch.uint8, device="cuda")
         cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
-        for q in (1024, 4096, 32768):
+        for q in (768, 1024, 1536, 2048, 4096, 32768):
             needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
             med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 20, cnt, algo=yp.ALGO_TENSOR_PAIRED), iters=5, warm=1)
             print(f"[{tag}] match 10M x {q:6d} paired: median {med / 1e3:9.2f} ms  {n * q / med / 1e6:8.3f} Tpairs/s  "
