@@ -178,20 +178,24 @@ def test_prefix_filter_boundaries(cuda, oracle, q):
 @pytest.mark.parametrize("q", [5, 300])
 def test_paired_accumulator_fields(cuda, oracle, q):
     """ALGO_TENSOR_PAIRED packs the prefix dot products of two rows of a 960-row super-tile into one f32 accumulator
-    as two s16 fields: rows c and c + W of a group of 2 W rows (W = 128, 112, 128, 112; groups start at 0, 256, 480,
-    736); the high field compares hash bits 6..127 only (bits 0..5 of byte 0 carry the bias constants).  Plant every
+    as two s16 fields: rows c and c + 240 of a group of 480 rows (groups start at 0 and 480; the older 128 / 112
+    geometry is still planted, it only spreads the columns); the high field does not see hash bits 0, 4, 8, 12, 16,
+    20 of word 0 (bits 0 and 4 of bytes 0..2), whose operand positions carry the bias constants.  Plant every
     combination of prefix distances in the two rows of one column -- including the ones that push the packed value
-    out of its exponent window (prefix distance < 32 or > 96 in the high row), a negative low field that borrows
-    from the high one, and differences confined to the six bias positions -- and require the exact match set."""
+    out of its exponent window, a negative low field that borrows from the high one, and differences confined to
+    the six bias positions -- and require the exact match set."""
     rng = np.random.default_rng(77 + q)
     n_rows = 960 * 40 + 123
     rows = oracle.synth_db(n_rows, first_row=11)
     needles = rng.integers(0, 256, size=(q, 32), dtype=np.uint8)
-    groups = [(0, 128), (256, 112), (480, 128), (736, 112)]
+    groups = [(0, 128), (256, 112), (480, 128), (736, 112), (0, 240), (480, 240)]
+    bias_pos = [(0, 0), (0, 4), (1, 0), (1, 4), (2, 0), (2, 4)]      # (byte, bit) of the six bias positions
 
-    def flip_bias_bits(h, k):        # flip k of the six lowest bits of byte 0
+    def flip_bias_bits(h, k):        # flip k of the six hash bits the high field does not see
         out = h.copy()
-        out[0] ^= np.uint8(sum(1 << int(b) for b in rng.choice(6, size=k, replace=False)))
+        for b in rng.choice(6, size=k, replace=False):
+            byte, bit = bias_pos[int(b)]
+            out[byte] ^= np.uint8(1 << bit)
         return out
 
     lo_cases = [(0, 0), (31, 0), (32, 0), (0, 31), (16, 15), (128, 0), (100, 3), (64, 0), (33, 0), (127, 0)]
@@ -201,7 +205,7 @@ def test_paired_accumulator_fields(cuda, oracle, q):
     for a in lo_cases:
         for b in hi_cases:
             st = (col * 7) % (n_rows // 960 - 1)
-            g0, w = groups[col % 4]
+            g0, w = groups[col % len(groups)]
             c = (col * 53) % w
             needle = needles[(col * 3) % q]
             rows[st * 960 + g0 + c] = _flip_in(needle, a[0], a[1], rng)                 # low field of the column
@@ -222,6 +226,57 @@ def test_paired_accumulator_fields(cuda, oracle, q):
         if q <= 8 or thr <= 36:
             assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_PAIRED, cap=1 << 18) == want, thr
         assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_FULL, cap=1 << 18) == want, thr
+
+
+def _with_prefix_popcount(rng, k, suffix=None):
+    """32-byte hash whose first 128 bits hold exactly k ones (random positions)."""
+    bits = np.zeros(256, dtype=np.uint8)
+    bits[rng.choice(128, size=k, replace=False)] = 1
+    bits[128:] = np.unpackbits(suffix)[128:] if suffix is not None else rng.integers(0, 2, size=128, dtype=np.uint8)
+    return np.packbits(bits)
+
+
+@pytest.mark.parametrize("thr", [31, 0, 12, 60])
+def test_paired_sparse_and_dense_operands(cuda, oracle, thr):
+    """The tensor matcher's rows are 0/1-valued operands (hash bits masked into place), so a prefix dot product is
+    popc(needle) - distance and the candidate minimum is per needle: it is NEGATIVE for needles with fewer set prefix
+    bits than the threshold (the all-zero hash of a flat frame is the realistic case), and a dense row in the high
+    field of the same accumulator column then moves the packed value below its exponent window, where the low field
+    reads doubled.  Plant sparse / dense / all-zero / all-one needles against sparse / dense / all-zero / all-one rows
+    in both fields of shared columns and require the exact match set from every tensor variant."""
+    rng = np.random.default_rng(4242 + thr)
+    n_rows = 960 * 56 + 77
+    rows = oracle.synth_db(n_rows, first_row=99)
+    pops = [0, 1, 5, 10, 20, 30, 31, 32, 33, 64, 96, 100, 127, 128]
+    needles = np.stack([_with_prefix_popcount(rng, k) for k in pops] +
+                       [np.zeros(32, np.uint8), np.full(32, 255, np.uint8)] +
+                       [rng.integers(0, 256, size=32, dtype=np.uint8) for _ in range(6)])
+    q = needles.shape[0]
+    zeros, ones = np.zeros(32, np.uint8), np.full(32, 255, np.uint8)
+    col = 0
+    for j in range(q):
+        for d in (0, max(thr - 10, 0), max(thr - 1, 0), thr, thr + 1, min(thr + 40, 128)):
+            near = _flip_in(needles[j], min(d, 128), 0, rng)            # prefix distance d, suffix equal
+            for other in (ones, zeros, _with_prefix_popcount(rng, 120), _with_prefix_popcount(rng, 3), None):
+                for near_is_low in (True, False):
+                    st, stage, c = col % 56, (col // 56) % 2, (col * 37) % 240     # distinct columns
+                    r_lo = st * 960 + stage * 480 + c
+                    a, b = (near, other) if near_is_low else (other, near)
+                    if a is not None:
+                        rows[r_lo] = a
+                    if b is not None:
+                        rows[r_lo + 240] = b
+                    col += 1
+    want = sorted(match_tuples(oracle.matcher_find(rows, needles, thr)))
+    assert len(want) > 400
+    m = cuda.CudaMatcher(cuda.CudaVectorDatabase(rows), thr)
+    for algo in (cuda.ALGO_TENSOR_PAIRED, cuda.ALGO_TENSOR_PREFIX, cuda.ALGO_TENSOR_FULL, cuda.ALGO_TENSOR, cuda.ALGO_AUTO,
+                 cuda.ALGO_TILED):
+        assert _find_device(cuda, m, needles, algo, cap=1 << 18) == want, algo
+    # the same needles padded to several tiles (the per-needle minima are indexed by tile)
+    many = np.concatenate([rng.integers(0, 256, size=(300, 32), dtype=np.uint8), needles])
+    want2 = sorted(match_tuples(oracle.matcher_find(rows, many, thr)))
+    assert _find_device(cuda, m, many, cuda.ALGO_TENSOR_PAIRED, cap=1 << 18) == want2
 
 
 def test_paired_needle_chunks(cuda, oracle):

@@ -133,12 +133,43 @@ def main():
             print(f"cross 1M x {q:4d} paired: median {med:9.1f} us")
             cnt.zero_()
         small.close()
-        for q in (8, 16, 32, 64, 128, 256, 512):
+        for q in (8, 16, 32, 64, 128, 256, 512, 1024, 2048):
             needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
-            for name, algo in (("tiled", yp.ALGO_TILED), ("paired", yp.ALGO_TENSOR_PAIRED)):
-                med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 20, cnt, algo=algo), iters=10, warm=2)
-                print(f"cross 10M x {q:4d} {name:6s}: median {med:9.1f} us  {n * q / med / 1e6:8.3f} Tpairs/s")
+            for name, algo in (("tiled", yp.ALGO_TILED), ("paired", yp.ALGO_TENSOR_PAIRED), ("auto", yp.ALGO_AUTO)):
+                if name == "tiled" and q > 256:
+                    continue
+                med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 20, cnt, algo=algo), iters=10, warm=2, flush=flush)
+                print(f"cross 10M x {q:4d} {name:6s}: median {med:9.1f} us  best {best:9.1f} us  {n * q / med / 1e6:8.3f} Tpairs/s  "
+                      f"{n * 32 / med / 1e3:7.1f} GB/s")
                 cnt.zero_()
+        db.close()
+    if "fixed" in what:   # fixed cost of a launch: tiny shards (one 960-row unit per SM and multiples)
+        out = torch.zeros((1 << 20, 16), dtype=torch.uint8, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for n in (960 * 148, 960 * 148 * 4, 960 * 148 * 16, 1_250_048, 10_000_384):
+            db = yp.CudaVectorDatabase(synthetic_rows=n)
+            m = yp.CudaMatcher(db, 31)
+            for q in (8, 128, 1024):
+                needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
+                for name, algo in (("tiled", yp.ALGO_TILED), ("paired", yp.ALGO_TENSOR_PAIRED)):
+                    if name == "tiled" and q > 128:
+                        continue
+                    med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 20, cnt, algo=algo), iters=20, warm=3, flush=flush)
+                    print(f"fixed {n:9d} rows x {q:4d} {name:6s}: median {med:8.1f} us  best {best:8.1f} us")
+            db.close()
+    if "prof" in what:    # a few launches of the <=128-needle scan for ncu
+        n = (10_000_000 // 2048 + 1) * 2048
+        db = yp.CudaVectorDatabase(synthetic_rows=n)
+        m = yp.CudaMatcher(db, 31)
+        out = torch.zeros((1 << 20, 16), dtype=torch.uint8, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for q in (8, 128):
+            needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
+            for algo in (yp.ALGO_TENSOR_PAIRED, yp.ALGO_TILED):
+                for _ in range(2):
+                    flush.sum()
+                    m.find_device(needles, q, out, 1 << 20, cnt, algo=algo)
+        torch.cuda.synchronize()
         db.close()
     if "hashpx" in what:   # hash kernel per pixel format
         k = yp.CudaKernel(0)

@@ -31,10 +31,10 @@ int ensure_device(int device)
         (void)cudaGetLastError();
         return YUME_PDQ_CUDA_E_NO_DEVICE;
     }
-    if (device < 0 || device >= count)
+    if (device < 0 || device >= count || device >= 64)   // per-device tables below and in api.cu hold 64 entries
         return YUME_PDQ_CUDA_E_INVALID;
     static std::atomic<int> checked[64];
-    if (device < 64 && checked[device].load() == 0) {
+    if (checked[device].load() == 0) {
         int major = 0;
         if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess ||
             major != 10) {
@@ -58,20 +58,35 @@ int ensure_device(int device)
 
 namespace {
 
-// grow-only device / pinned scratch, one set per host thread and device
+// grow-only device / pinned scratch, one set per (host thread, device, purpose); freed at thread exit
+constexpr int kMaxDevices = 64;
 struct Scratch {
     void *dev = nullptr;
     size_t dev_bytes = 0;
     void *pin = nullptr;
     size_t pin_bytes = 0;
     int device = -1;
+    ~Scratch()
+    {
+        if (!dev && !pin)
+            return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) {
+            (void)cudaGetLastError();   // runtime already torn down at process exit: nothing left to free
+            return;
+        }
+        if (dev)
+            cudaFree(dev);
+        if (pin)
+            cudaFreeHost(pin);
+        if (cur >= 0)
+            cudaSetDevice(cur);
+        (void)cudaGetLastError();
+    }
+    // the current device is `device_` (ensure_device ran)
     int reserve(int device_, size_t d, size_t p)
     {
-        if (device != device_) {  // other device: drop (the old allocations stay with their device)
-            dev = pin = nullptr;
-            dev_bytes = pin_bytes = 0;
-            device = device_;
-        }
+        device = device_;
         if (d > dev_bytes) {
             if (dev)
                 cudaFree(dev);
@@ -100,10 +115,54 @@ struct Scratch {
     }
 };
 
-Scratch &tls_scratch(int which)
+// A host thread that round-robins over several GPUs keeps one scratch set per device (ensure_device has already
+// rejected device >= kMaxDevices... it accepts any index the runtime reports, so clamp here).
+Scratch &tls_scratch(int which, int device)
 {
-    static thread_local Scratch s[4];
-    return s[which];
+    static thread_local Scratch s[2][kMaxDevices];
+    return s[which][(unsigned)device % kMaxDevices];
+}
+
+// copy stream + events of the chunked host-frame pipeline, per (host thread, device)
+struct CopyCtx {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+    int device = -1;
+    int init(int device_)
+    {
+        if (stream)
+            return 0;
+        device = device_;
+        YPDQ_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            YPDQ_CUDA_TRY(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+            YPDQ_CUDA_TRY(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        }
+        return 0;
+    }
+    ~CopyCtx()
+    {
+        if (!stream)
+            return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return;
+        }
+        for (int i = 0; i < 2; i++) {
+            if (copied[i]) cudaEventDestroy(copied[i]);
+            if (done[i]) cudaEventDestroy(done[i]);
+        }
+        cudaStreamDestroy(stream);
+        if (cur >= 0)
+            cudaSetDevice(cur);
+        (void)cudaGetLastError();
+    }
+};
+CopyCtx &tls_copy_ctx(int device)
+{
+    static thread_local CopyCtx c[kMaxDevices];
+    return c[(unsigned)device % kMaxDevices];
 }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -119,6 +178,7 @@ struct Stager {
     std::vector<Out> outs;
     uint8_t *base = nullptr;
     size_t off = 0;
+    bool staged_in = false;   // a host input went through the thread's scratch block
     explicit Stager(cudaStream_t s_) : s(s_) {}
     template <class T>
     int in(const T *p, size_t bytes, const T **dp)
@@ -130,6 +190,7 @@ struct Stager {
         T *d = reinterpret_cast<T *>(base + off);
         off += align_up(bytes, 256);
         YPDQ_CUDA_TRY(cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, s));
+        staged_in = true;
         *dp = d;
         return 0;
     }
@@ -149,7 +210,9 @@ struct Stager {
     {
         for (auto &o : outs)
             YPDQ_CUDA_TRY(cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, s));
-        if (!outs.empty())
+        // any call with a host pointer returns after completion (yume_pdq_cuda.h): the caller may reuse its
+        // buffers, and the thread's scratch block may be overwritten by its next call on another stream
+        if (!outs.empty() || staged_in)
             YPDQ_CUDA_TRY(cudaStreamSynchronize(s));
         return 0;
     }
@@ -255,7 +318,7 @@ bool yume_pdq_visit_dihedrals_smart_kernel(void *ctx, float threshold, uint8_t *
     const int device = default_device();
     if (!output || !pdqf || !callback || ensure_device(device) != 0)
         return false;
-    Scratch &sc = tls_scratch(1);
+    Scratch &sc = tls_scratch(1, device);
     if (sc.reserve(device, 16 * 1024, 16 * 1024) != 0)
         return false;
     float *d_p = reinterpret_cast<float *>(sc.dev);
@@ -342,17 +405,14 @@ int hash_chunks(int device, const void *frames_v, int fmt, size_t n, uint8_t *d_
         return rc ? rc : after_chunk((size_t)0, n);
     }
     uint8_t *d_in[2] = {static_cast<uint8_t *>(d_in0), static_cast<uint8_t *>(d_in0) + chunk * fb};
-    static thread_local cudaStream_t copy_stream = nullptr;
-    static thread_local cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-    static thread_local int ev_dev = -1;
-    if (ev_dev != device) {
-        YPDQ_CUDA_TRY(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; i++) {
-            YPDQ_CUDA_TRY(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
-            YPDQ_CUDA_TRY(cudaEventCreateWithFlags(&ev_done[i], cudaEventDisableTiming));
-        }
-        ev_dev = device;
+    CopyCtx &cc = tls_copy_ctx(device);
+    {
+        const int rc0 = cc.init(device);
+        if (rc0)
+            return rc0;
     }
+    cudaStream_t copy_stream = cc.stream;
+    cudaEvent_t *ev_copied = cc.copied, *ev_done = cc.done;
     // the copy stream must not start overwriting scratch still in use by earlier work on s
     YPDQ_CUDA_TRY(cudaEventRecord(ev_done[0], s));
     YPDQ_CUDA_TRY(cudaStreamWaitEvent(copy_stream, ev_done[0], 0));
@@ -432,7 +492,7 @@ int yume_pdq_cuda_hash_batch_pixels(int device, const void *frames, int pixel_fo
     cudaStream_t s = (cudaStream_t)stream;
     const bool frames_on_host = !is_device_ptr(frames);
     // outputs: staged through one scratch block when they live on the host
-    Scratch &so = tls_scratch(0);
+    Scratch &so = tls_scratch(0, device);
     size_t out_need = host_bytes(hashes, n * 256) + host_bytes(quality, n * 32) +
                       host_bytes(thresholds, n * 32) + host_bytes(pdqf, n * 1024);
     const size_t chunk = std::min<size_t>(n, 64);  // frames per H2D chunk (64 MiB of f32)
@@ -466,7 +526,7 @@ int yume_pdq_cuda_hash_batch_pixels(int device, const void *frames, int pixel_fo
     if (rc)                                                                      \
         return rc;                                                               \
     cudaStream_t s = (cudaStream_t)stream;                                       \
-    Scratch &so = tls_scratch(0);                                                \
+    Scratch &so = tls_scratch(0, device);                                        \
     rc = so.reserve(device, (total_host_bytes) + 4096, 0);                       \
     if (rc)                                                                      \
         return rc;                                                               \
@@ -910,7 +970,7 @@ int yume_pdq_cuda_screen_batch_pixels(YumePDQ_CudaDb *db, const void *frames, in
     const bool frames_on_host = !is_device_ptr(frames);
     // device staging: hashes always (they are the needles), quality if wanted on the host, frame chunks
     const size_t chunk = std::min<size_t>(n, 128);   // frames per pipeline step: 128 MiB of f32 H2D, 1024 needles
-    Scratch &so = tls_scratch(1);
+    Scratch &so = tls_scratch(1, device);
     const bool hashes_dev = hashes && is_device_ptr(hashes);
     const size_t need = (hashes_dev ? 0 : align_up(n * 256, 256)) + host_bytes(quality, n * 32) +
                         (frames_on_host ? 2 * chunk * fb : 0) + 4096;

@@ -70,6 +70,21 @@ int launch_dihedrals(const float *pdqf, const float *thr0, size_t n, uint8_t *ha
                      float *thresholds, cudaStream_t s);
 
 enum MatchMode : int { MODE_LIST = 0, MODE_MIN = 1 };
+
+// The match counter of the C ABI is 32 bits wide.  Reserving slots must never wrap it (32768 needles x 10M rows at a
+// threshold near 128 match more than 2^32 pairs): from YPDQ_COUNT_SATURATED on a reservation is taken back, so the
+// counter stays put just above that value, the host sees count > capacity and reports YUME_PDQ_CUDA_E_CAPACITY
+// (n_found is then a lower bound).  Fewer than 2^28 reservations can be in flight at once, so it cannot wrap.
+#define YPDQ_COUNT_SATURATED 0xF0000000u
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t reserve_matches(uint32_t *count, uint32_t n)
+{
+    const uint32_t pos = atomicAdd(count, n);
+    if (pos >= YPDQ_COUNT_SATURATED)
+        atomicSub(count, n);
+    return pos;
+}
+#endif
 int launch_match(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
                  size_t q, uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
                  unsigned long long *min_key, int mode, int algo, int sm_count, cudaStream_t s,

@@ -85,7 +85,7 @@ struct Sink {
 __device__ __forceinline__ void emit_single(const Sink &k, uint64_t local_row, uint32_t needle,
                                             uint32_t dist)
 {
-    uint32_t pos = atomicAdd(k.count, 1u);
+    uint32_t pos = reserve_matches(k.count, 1u);
     if (k.mode == MODE_MIN) {
         atomicMin(k.min_key, (unsigned long long)(local_row * k.q + needle));
     } else if (pos < k.cap) {
@@ -109,7 +109,7 @@ __device__ __forceinline__ void emit_ballot(const Sink &k, bool hit, uint64_t lo
     const int leader = __ffs(b) - 1;
     uint32_t base = 0;
     if ((int)lane == leader)
-        base = atomicAdd(k.count, (uint32_t)__popc(b));
+        base = reserve_matches(k.count, (uint32_t)__popc(b));
     base = __shfl_sync(full, base, leader);
     if (hit) {
         if (k.mode == MODE_MIN) {
@@ -425,13 +425,13 @@ int launch_match(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const 
     const uint4 *rows4 = reinterpret_cast<const uint4 *>(rows);
     const uint4 *needles4 = reinterpret_cast<const uint4 *>(needles);
     if (algo == YUME_PDQ_CUDA_ALGO_AUTO) {
-        // Measured on B200 (10M rows, threshold 31; profiles/r01ag): tiled POPC kernel 54 us for 8 needles, 86 us for
-        // 16, 156 us for 32, 302 us for 64 (2.1e12 pairs/s from there on); paired tensor kernel ~170 us for anything up
-        // to 128 needles (one needle tile: the row expansion is the floor), 190 us for 256, 254 us for 512, 0.45 ms for
-        // 1024.  Above threshold 36 the tensor path is the unpaired full kernel (1024 needles 0.8 ms vs tiled 4.7 ms);
-        // the 96-bit prefix bound of the POPC kernels stops filtering once threshold approaches 48.
-        // (a persistent tensor launch costs ~20 us before the first row: not for tiny shards)
-        if (q >= (threshold <= 36 ? 48u : 512u) && (q >= 512 || n_rows >= 100000))
+        // Measured on B200 (10M rows, threshold 31; profiles/r02*/quick.log): tiled POPC kernel 54 us for 8 needles, 86 us
+        // for 16, 157 us for 32 (2.1e12 pairs/s from there on); paired tensor kernel 74..86 us for anything up to 128
+        // needles (one launch, X2One), 142 us for 256, 230 us for 512, 0.39 ms for 1024.  Above threshold 36 the tensor
+        // path is the unpaired full kernel (1024 needles 0.8 ms vs tiled 4.7 ms); the 96-bit prefix bound of the POPC
+        // kernels stops filtering once the threshold approaches 48.
+        // (a persistent tensor launch costs ~12 us before the first row: not for tiny shards)
+        if (q >= (threshold <= 36 ? 14u : 512u) && (q >= 512 || n_rows >= 100000))
             algo = YUME_PDQ_CUDA_ALGO_TENSOR;
         else if (threshold > 40)
             algo = YUME_PDQ_CUDA_ALGO_EXACT;

@@ -133,7 +133,7 @@ struct TcSink {
 
 __device__ __forceinline__ void tc_emit(const TcSink &k, uint64_t local_row, uint32_t needle, uint32_t dist)
 {
-    uint32_t pos = atomicAdd(k.count, 1u);
+    uint32_t pos = reserve_matches(k.count, 1u);
     if (k.mode == MODE_MIN) {
         atomicMin(k.min_key, (unsigned long long)(local_row * k.q + needle));
     } else if (pos < k.cap) {

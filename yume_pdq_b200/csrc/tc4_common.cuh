@@ -91,6 +91,27 @@ __device__ __forceinline__ uint4 expand32(uint32_t w)
     return make_uint4(expand8(w & 255u), expand8((w >> 8) & 255u), expand8((w >> 16) & 255u), expand8(w >> 24));
 }
 
+// MASKED operand encoding (matcher_tc4x2.cu): database rows are NOT expanded bit by bit.  A nibble with a single bit
+// set is an e2m1 value on its own (0x1 = 0.5, 0x2 = 1.0, 0x4 = 2.0), so ANDing a hash word with 0x1111.., 0x2222..,
+// 0x4444.. yields three operand words whose elements are {0, s} -- hash bit 4i + j of the word in nibble i of chunk
+// word j, scaled by s_j = 0.5, 1, 2 -- and bit 4i + 3 (the e2m1 sign position) is moved down by one first.  Five
+// integer instructions per hash word instead of ~40.  The needle side (expanded once per launch) carries the sign
+// and the inverse scale: element = +1/s_j where the needle bit is 1, -1/s_j where it is 0, so that
+//     dot(needle, row) = popc(row & needle) - popc(row & ~needle) = popc(needle) - hamming(needle, row)
+// exactly (all products are +-1 or 0, sums are small integers).
+__device__ __forceinline__ uint4 mask32(uint32_t w)
+{
+    return make_uint4(w & 0x11111111u, w & 0x22222222u, w & 0x44444444u, (w >> 1) & 0x44444444u);
+}
+__device__ __forceinline__ uint4 needle32(uint32_t v)
+{
+    const uint32_t n = ~v;   // sign bit (nibble bit 3) where the needle bit is 0
+    return make_uint4(0x44444444u | ((n & 0x11111111u) << 3),    // +-2.0 against the row's 0.5
+                      0x22222222u | ((n & 0x22222222u) << 2),    // +-1.0 against 1.0
+                      0x11111111u | ((n & 0x44444444u) << 1),    // +-0.5 against 2.0
+                      0x11111111u | (n & 0x88888888u));          // +-0.5 against 2.0 (bit 4i + 3, moved down in the row)
+}
+
 struct Tc4Sink {
     YumePDQ_Match *out;
     uint32_t cap;
@@ -106,7 +127,7 @@ struct Tc4Sink {
 
 __device__ __forceinline__ void tc4_emit(const Tc4Sink &k, uint64_t local_row, uint32_t needle, uint32_t dist)
 {
-    uint32_t pos = atomicAdd(k.count, 1u);
+    uint32_t pos = reserve_matches(k.count, 1u);
     if (k.mode == MODE_MIN) {
         atomicMin(k.min_key, (unsigned long long)(local_row * k.q + needle));
     } else if (pos < k.cap) {
