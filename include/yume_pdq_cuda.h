@@ -30,59 +30,21 @@
 #include <stddef.h>
 #include <stdint.h>
 
+/* ------------------------------------------------------------------ (A) --
+ * The reference's own ABI: version symbols, YumePDQ_Dihedrals and its 8 constants, DihedralCallback,
+ * yume_pdq_hash_smart_kernel, yume_pdq_visit_dihedrals_smart_kernel. */
+#include "yume_pdq.h"
+
 #ifdef __cplusplus
 extern "C" {
 #endif
-
-/* ------------------------------------------------------------------ (A) --
- * Reference ABI, include/yume_pdq.h:22-25 / build.rs:389-429 */
-extern const uint32_t YUME_PDQ_VERSION_MAJOR;
-extern const uint32_t YUME_PDQ_VERSION_MINOR;
-extern const uint32_t YUME_PDQ_VERSION_PATCH;
-extern const char YUME_PDQ_VERSION_STRING[];
-
-/* include/yume_pdq.h:46-56 / src/lib.rs:85-134: big-endian i8 [dx.0, dx.1, dy.0, dy.1] */
-typedef struct YumePDQ_Dihedrals {
-    uint32_t packed;
-} YumePDQ_Dihedrals;
-
-/* include/yume_pdq.h:62-100 / src/lib.rs:154-177 */
-extern const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_NORMAL;
-extern const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_FLIPPED;
-extern const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_FLOPPED;
-extern const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_ROTATED_180;
-extern const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_ROTATED_90;
-extern const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_ROTATED_270;
-extern const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_ROTATED_90_FLOPPED;
-extern const struct YumePDQ_Dihedrals YUME_PDQ_DIHEDRAL_FLOPPED_ROTATED_270;
-
-/* include/yume_pdq.h:44 / src/lib.rs:186-187 */
-typedef bool (*DihedralCallback)(void *ctx, uint32_t dihedral, float threshold, float quality);
-
-/* include/yume_pdq.h:120-125 / src/lib.rs:251-283 (hash_get_threshold, lib.rs:427-455).
- * input 512*512 f32 row-major; threshold nullable; output 32 bytes; buf1 128*128
- * f32 (receives the 127x127 tent-filtered image, zero padded); tmp 128 f32
- * (scratch, left untouched by this implementation); pdqf 256 f32.  Returns the
- * quality in [0,1]; NaN if no CUDA device is usable (the reference has no error
- * channel here). Runs on device 0 (or $YUME_PDQ_CUDA_DEVICE). */
-float yume_pdq_hash_smart_kernel(const float *input, float *threshold, uint8_t *output, float *buf1,
-                                 float *tmp, float *pdqf);
-
-/* include/yume_pdq.h:143-147 / src/lib.rs:205-232 (visit_dihedrals, lib.rs:358-420).
- * Calls `callback` 7 times in the order FLOPPED, ROTATED_180, FLIPPED,
- * ROTATED_90_FLOPPED, ROTATED_270, FLOPPED_ROTATED_270, ROTATED_90; during each
- * call `output` holds that dihedral's hash and `pdqf` its transformed PDQF.  The
- * callback receives the ORIGINAL `threshold` argument every time (lib.rs:223-224).
- * Returns false iff the callback returned false (or no device is usable); pdqf
- * is left in the state of the last visited dihedral (C.P^T after all seven). */
-bool yume_pdq_visit_dihedrals_smart_kernel(void *ctx, float threshold, uint8_t *output, float *pdqf,
-                                           DihedralCallback callback);
 
 /* ------------------------------------------------------------------ (B) -- */
 #define YUME_PDQ_CUDA_OK 0
 #define YUME_PDQ_CUDA_E_INVALID (-1)   /* bad argument (NULL, size, q == 0, ...) */
 #define YUME_PDQ_CUDA_E_NO_DEVICE (-2) /* no usable CUDA device / not an sm_100 part */
-#define YUME_PDQ_CUDA_E_CAPACITY (-3)  /* more matches than `cap`; *n_found holds the total */
+#define YUME_PDQ_CUDA_E_CAPACITY (-3)  /* more matches than `cap`; *n_found holds the total (a lower bound once the
+                                        * 32-bit device counter saturates at 0xF0000000 matches) */
 #define YUME_PDQ_CUDA_E_NOMEM (-4)
 
 const char *yume_pdq_cuda_error_string(int code);

@@ -467,6 +467,16 @@ API int cpu_baseline_hw_threads(void)
     return n ? (int)n : 1;
 }
 
+/* Avx2F32Kernel::quantize (x86.rs:440-621) on one 16x16 PDQF: bisection threshold + 32 hash bytes.
+ * Returns 0, or -1 when the host has no AVX2+FMA. */
+API int cpu_baseline_quantize_avx2(const float *pdqf, float *threshold, uint8_t *out)
+{
+    if (!have_avx2())
+        return -1;
+    quantize_avx2(pdqf, threshold, out);
+    return 0;
+}
+
 /* Hash n frames (8 dihedral hashes each) with the AVX2 kernel on `threads` threads.
  * hashes [n][8][32], quality [n][8], thresholds [n][8], pdqf [n][256] or NULL.
  * Returns 0, or -1 when the host has no AVX2+FMA. */

@@ -283,6 +283,8 @@ class CpuBaseline:
         L.cpu_baseline_match.argtypes = [_u8p, C.c_size_t, _u8p, C.c_size_t, C.c_uint32, C.c_int,
                                          C.POINTER(Match), C.c_size_t, C.c_int, C.c_int]
         L.cpu_baseline_match.restype = C.c_size_t
+        L.cpu_baseline_quantize_avx2.argtypes = [_f32p, _f32p, _u8p]
+        L.cpu_baseline_quantize_avx2.restype = C.c_int
         self.isa = L.cpu_baseline_isa()
         self.hw_threads = L.cpu_baseline_hw_threads()
 
@@ -306,6 +308,15 @@ class CpuBaseline:
         if rc != 0:
             raise RuntimeError("host CPU has no AVX2+FMA")
         return hashes, quality, thr, pdqf
+
+    def quantize_avx2(self, pdqf):
+        """Avx2F32Kernel::quantize (x86.rs:440-621): (hash [32] u8, bisection threshold)."""
+        pdqf = np.ascontiguousarray(pdqf, dtype=np.float32).reshape(256)
+        thr = np.zeros(1, dtype=np.float32)
+        out = np.zeros(32, dtype=np.uint8)
+        if self.lib.cpu_baseline_quantize_avx2(_fp(pdqf), _fp(thr), _bp(out)) != 0:
+            raise RuntimeError("host CPU has no AVX2+FMA")
+        return out, np.float32(thr[0])
 
     def match(self, rows, needles, threshold: int, find: bool = True, threads: int = 1,
               force_scalar: bool = False, cap: int = 1 << 20):

@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "yume_pdq_cuda.h")).read()
+    text = (open(os.path.join(ROOT, "include", "yume_pdq.h")).read() +
+            open(os.path.join(ROOT, "include", "yume_pdq_cuda.h")).read())
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     funcs = set(re.findall(r"\b(yume_pdq_[a-z0-9_]+)\s*\(", text))
     data = set(re.findall(r"extern const [^;]*?\b(YUME_PDQ_[A-Z0-9_]+)\s*(?:\[\d*\])?;", text))

@@ -43,6 +43,7 @@ PIXEL_F32, PIXEL_LUMA8, PIXEL_RGB8, PIXEL_RGBA8, PIXEL_FMA = 0, 1, 2, 3, 0x100
 RGB8_TO_LUMA8_TABLE_ITU = (0.299, 0.587, 0.114)
 
 E_INVALID, E_NO_DEVICE, E_CAPACITY, E_NOMEM = -1, -2, -3, -4
+COUNT_SATURATED = 0xF0000000    # the device-side match counter stops here (csrc/common.cuh)
 
 
 class YumePdqCudaError(RuntimeError):
@@ -499,6 +500,8 @@ class CudaMatcher:
             rc = lib.yume_pdq_cuda_matcher_find(self.haystack._h, _ptr(query), q, self.threshold,
                                                 _ptr(out), cap, C.byref(n), _stream(self.stream))
             if rc == E_CAPACITY:
+                if n.value >= COUNT_SATURATED:
+                    raise YumePdqCudaError(rc, "matcher_find (more than 4e9 matches: the 32-bit device counter saturated)")
                 cap = int(n.value)
                 continue
             _check(rc, "matcher_find")
@@ -537,6 +540,8 @@ class CudaMatcher:
                                                        self.threshold, _ptr(hashes), _ptr(quality), _ptr(out),
                                                        cap, C.byref(k), _stream(self.stream))
             if rc == E_CAPACITY:
+                if k.value >= COUNT_SATURATED:
+                    raise YumePdqCudaError(rc, "screen_batch (more than 4e9 matches: the 32-bit device counter saturated)")
                 cap = int(k.value)
                 continue
             _check(rc, "screen_batch")

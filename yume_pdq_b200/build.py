@@ -9,6 +9,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libyume_pdq_cuda.so")
+# the reference's library name (Cargo.toml: crate `yume_pdq`, cdylib -> libyume_pdq.so): existing users link `-lyume_pdq`
+# or load it through $LIBYUME_PDQ_PATH (integration/hash.py:32) and find this implementation
+LIB_ALIAS = os.path.join(HERE, "libyume_pdq.so")
 CLI_SRC = os.path.join(HERE, "cli")
 CLI = os.path.join(HERE, "yume-pdq-cuda")     # `pipe` front end (cli/yume_pdq_pipe.cpp), links only the C ABI
 SOURCES = ["api.cu", "hasher.cu", "matcher.cu", "matcher_tc.cu", "matcher_tc4.cu", "matcher_tc4x2.cu", "synth.cu", "peak.cu"]
@@ -30,7 +33,7 @@ def needs_build() -> bool:
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    deps += [os.path.join(HERE, "..", "include", f) for f in ("yume_pdq_cuda.h", "yume_pdq_luts.h")]
+    deps += [os.path.join(HERE, "..", "include", f) for f in ("yume_pdq.h", "yume_pdq_cuda.h", "yume_pdq_luts.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -60,8 +63,17 @@ def build_cli(force: bool = False) -> str:
     return CLI
 
 
+def link_alias() -> None:
+    if os.path.islink(LIB_ALIAS) and os.readlink(LIB_ALIAS) == os.path.basename(LIB):
+        return
+    if os.path.lexists(LIB_ALIAS):
+        os.remove(LIB_ALIAS)
+    os.symlink(os.path.basename(LIB), LIB_ALIAS)
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
+        link_alias()
         build_cli()
         return LIB
     cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
@@ -74,6 +86,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed")
     if verbose:
         print(log)
+    link_alias()
     build_cli(force=True)
     return LIB
 

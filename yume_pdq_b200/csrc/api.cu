@@ -119,7 +119,7 @@ struct Scratch {
 // rejected device >= kMaxDevices... it accepts any index the runtime reports, so clamp here).
 Scratch &tls_scratch(int which, int device)
 {
-    static thread_local Scratch s[2][kMaxDevices];
+    static thread_local Scratch s[3][kMaxDevices];
     return s[which][(unsigned)device % kMaxDevices];
 }
 
@@ -297,19 +297,53 @@ float yume_pdq_hash_smart_kernel(const float *input, float *threshold, uint8_t *
                                  float *tmp, float *pdqf)
 {
     (void)tmp;  // scratch in the reference; not needed here and left untouched
+    const float nan = std::numeric_limits<float>::quiet_NaN();
     const int device = default_device();
     if (!input || !output || !buf1 || !pdqf || ensure_device(device) != 0)
-        return std::numeric_limits<float>::quiet_NaN();
-    // hash_get_threshold, src/lib.rs:427-455
-    uint8_t hashes[256];
-    float quality[8], thr[8];
-    if (yume_pdq_cuda_jarosz_compress(device, input, 1, buf1, nullptr) != 0 ||
-        yume_pdq_cuda_hash_batch(device, input, 1, hashes, quality, thr, pdqf, nullptr) != 0)
-        return std::numeric_limits<float>::quiet_NaN();
-    std::memcpy(output, hashes, 32);
+        return nan;
+    // hash_get_threshold, src/lib.rs:427-455, as a latency path: ONE upload of the frame, the per-stage kernels
+    // (the tent filter spreads over 128 CTAs; the fused batch kernel would stream the frame through a single CTA),
+    // ONE download of {buf1, pdqf, threshold, quality, hash}, one synchronisation.
+    struct Out {
+        float buf1[128 * 128];
+        float pdqf[256];
+        float thr, quality, gradient, thr_avx2;
+        uint8_t hash[32];
+    };
+    Scratch &sc = tls_scratch(2, device);
+    if (sc.reserve(device, 512 * 512 * 4 + sizeof(Out) + 512, sizeof(Out)) != 0)
+        return nan;
+    cudaStream_t s = nullptr;
+    const float *d_in = input;
+    Out *d_out = reinterpret_cast<Out *>(sc.dev);
+    if (!is_device_ptr(input)) {
+        float *d_frame = reinterpret_cast<float *>(static_cast<uint8_t *>(sc.dev) + align_up(sizeof(Out), 256));
+        if (cudaMemcpyAsync(d_frame, input, 512 * 512 * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return nan;
+        }
+        d_in = d_frame;
+    }
+    // README.md:164-168 prints the AVX2 kernel's bisection threshold; opt in with YUME_PDQ_CUDA_THRESHOLD=avx2
+    const char *style = std::getenv("YUME_PDQ_CUDA_THRESHOLD");
+    const bool avx2_style = style && std::strcmp(style, "avx2") == 0;
+    if (launch_jarosz(d_in, 1, d_out->buf1, s) != 0 || launch_dct2d(d_out->buf1, 1, d_out->pdqf, s) != 0 ||
+        launch_quantize(d_out->pdqf, 1, &d_out->thr, d_out->hash, s) != 0 ||
+        launch_gradients(d_out->pdqf, 1, &d_out->gradient, &d_out->quality, s) != 0 ||
+        (avx2_style && launch_avx2_style_threshold(d_out->pdqf, &d_out->thr_avx2, s) != 0))
+        return nan;
+    Out *h = reinterpret_cast<Out *>(sc.pin);
+    if (cudaMemcpyAsync(h, d_out, sizeof(Out), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nan;
+    }
+    std::memcpy(buf1, h->buf1, sizeof h->buf1);
+    std::memcpy(pdqf, h->pdqf, sizeof h->pdqf);
+    std::memcpy(output, h->hash, 32);
     if (threshold)
-        *threshold = thr[0];
-    return quality[0];
+        *threshold = avx2_style ? h->thr_avx2 : h->thr;
+    return h->quality;
 }
 
 bool yume_pdq_visit_dihedrals_smart_kernel(void *ctx, float threshold, uint8_t *output, float *pdqf,
@@ -855,11 +889,17 @@ static int match_host(YumePDQ_CudaDb *db, const uint8_t *needles, size_t q, uint
             *min_key = res.min;
         if (mode != MODE_LIST)
             return 0;
+        if (res.count >= YPDQ_COUNT_SATURATED)   // more than ~4e9 matches: the 32-bit counter stopped counting
+            return YUME_PDQ_CUDA_E_CAPACITY;
         if (res.count > dev_cap) {  // rare: grow the device list and rescan so the sorted prefix is exact
             cap = res.count;
             continue;
         }
-        hits->resize(res.count);
+        try {
+            hits->resize(res.count);
+        } catch (const std::bad_alloc &) {
+            return YUME_PDQ_CUDA_E_NOMEM;
+        }
         if (res.count)
             YPDQ_CUDA_TRY(cudaMemcpy(hits->data(), db->d_out, res.count * sizeof(YumePDQ_Match),
                                      cudaMemcpyDeviceToHost));
@@ -894,9 +934,9 @@ int yume_pdq_cuda_matcher_find(YumePDQ_CudaDb *db, const uint8_t *needles, size_
     size_t total = 0;
     int rc = match_host(db, needles, q, threshold, MODE_LIST, &hits, cap, &total, nullptr,
                         (cudaStream_t)stream);
+    *n_found = total;     // also on YUME_PDQ_CUDA_E_CAPACITY from a saturated counter (a lower bound then)
     if (rc)
         return rc;
-    *n_found = total;
     const size_t k = std::min(cap, hits.size());
     if (k)
         std::memcpy(out, hits.data(), k * sizeof(YumePDQ_Match));
@@ -1033,11 +1073,18 @@ int yume_pdq_cuda_screen_batch_pixels(YumePDQ_CudaDb *db, const void *frames, in
         Init res;
         std::memcpy(&res, db->h_pin, 16);
         *n_found = res.count;
+        if (res.count >= YPDQ_COUNT_SATURATED)   // the 32-bit counter stopped counting: *n_found is a lower bound
+            return YUME_PDQ_CUDA_E_CAPACITY;
         if (res.count > dev_cap && attempt == 0) {
             list_cap = res.count;   // the sorted prefix must be exact: grow and rescan
             continue;
         }
-        std::vector<YumePDQ_Match> hits(std::min<size_t>(res.count, dev_cap));
+        std::vector<YumePDQ_Match> hits;
+        try {
+            hits.resize(std::min<size_t>(res.count, dev_cap));
+        } catch (const std::bad_alloc &) {
+            return YUME_PDQ_CUDA_E_NOMEM;
+        }
         if (!hits.empty())
             YPDQ_CUDA_TRY(cudaMemcpy(hits.data(), db->d_out, hits.size() * sizeof(YumePDQ_Match),
                                      cudaMemcpyDeviceToHost));

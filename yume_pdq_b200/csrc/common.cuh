@@ -60,6 +60,7 @@ inline size_t frame_bytes(int pixel_format)
     }
 }
 int launch_jarosz(const float *frames, size_t n, float *buf1, cudaStream_t s);
+int launch_avx2_style_threshold(const float *pdqf, float *out, cudaStream_t s);
 int launch_dct2d(const float *buf1, size_t n, float *pdqf, cudaStream_t s);
 int launch_gradients(const float *pdqf, size_t n, float *gradient, float *quality, cudaStream_t s);
 int launch_quantize(const float *pdqf, size_t n, float *thresholds, uint8_t *hashes, cudaStream_t s);

@@ -28,6 +28,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <mutex>
 #include <type_traits>
 
 #include "../../include/yume_pdq_luts.h"
@@ -589,10 +591,17 @@ cvt_luma8f_kernel(const uint8_t *__restrict__ px, size_t n_pixels, float cr, flo
 
 int upload_luts()
 {
-    static thread_local int done_dev = -1;
+    // once per device and process (the symbols live in the device's context, not in the calling thread)
+    static std::atomic<int> done[64];
+    static std::mutex mu;
     int dev = 0;
     YPDQ_CUDA_TRY(cudaGetDevice(&dev));
-    if (done_dev == dev)
+    if (dev < 0 || dev >= 64)
+        return YUME_PDQ_CUDA_E_INVALID;
+    if (done[dev].load(std::memory_order_acquire))
+        return 0;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[dev].load(std::memory_order_acquire))
         return 0;
     static uint32_t dt[127 * 16];
     for (int k = 0; k < 16; k++)
@@ -600,8 +609,67 @@ int upload_luts()
             dt[k2 * 16 + k] = YUME_PDQ_DCT_MATRIX_BITS[k * 127 + k2];
     YPDQ_CUDA_TRY(cudaMemcpyToSymbol(g_dt, dt, sizeof dt));
     YPDQ_CUDA_TRY(cudaMemcpyToSymbol(c_tent_bits, YUME_PDQ_TENT_WEIGHT_BITS, sizeof(uint32_t) * 49));
-    done_dev = dev;
+    done[dev].store(1, std::memory_order_release);
     return 0;
+}
+
+// The `threshold` value the reference's AVX2 / AVX-512 kernels report (x86.rs:440-621): not the lower median but the
+// point where a mean-of-the-residual-side bisection stops, anywhere in [sorted[127], sorted[128]).  The hash bits are
+// the same; callers that print the float see a different number (README.md:164-168: 12.554 where Torben gives
+// 11.907).  Lanes 0..7 of one warp play the eight lanes of a __m256, in the reference's operation order.
+__global__ void __launch_bounds__(32)
+avx2_style_threshold_kernel(const float *__restrict__ pdqf, float *__restrict__ out)
+{
+    const unsigned full = 0xffffffffu;
+    const int l = threadIdx.x & 7;
+    auto hsum8 = [&](float a) {     // horizontal!(sum ..): ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7)) in lane 0
+        a = __fadd_rn(a, __shfl_sync(full, a, (l + 1) & 7, 8));
+        a = __fadd_rn(a, __shfl_sync(full, a, (l + 2) & 7, 8));
+        a = __fadd_rn(a, __shfl_sync(full, a, (l + 4) & 7, 8));
+        return __shfl_sync(full, a, 0, 8);
+    };
+    float mx = -3.40282347e+38f, mn = 3.40282347e+38f;
+    for (int c = 0; c < 32; c++) {
+        const float v = pdqf[8 * c + l];
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+    }
+    for (int d = 1; d < 8; d <<= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(full, mx, d, 8));
+        mn = fminf(mn, __shfl_xor_sync(full, mn, d, 8));
+    }
+    float guess = __fmul_rn(__fadd_rn(mn, mx), 0.5f);
+    uint32_t num_over = 0, num_under = 0;
+    for (int iter = 0; iter < 32; iter++) {
+        float rs_gt = 0.0f, rs_lt = 0.0f;
+        uint32_t gt = 0, lt = 0;
+        for (int c = 0; c < 32; c++) {
+            const float v = pdqf[8 * c + l];
+            const bool mgt = v > guess && v <= mx, mlt = v < guess && v >= mn;
+            gt += mgt;
+            lt += mlt;
+            rs_gt = __fadd_rn(rs_gt, mgt ? v : 0.0f);
+            rs_lt = __fadd_rn(rs_lt, mlt ? v : 0.0f);
+        }
+        for (int d = 1; d < 8; d <<= 1) {
+            gt += __shfl_xor_sync(full, gt, d, 8);
+            lt += __shfl_xor_sync(full, lt, d, 8);
+        }
+        const float s_gt = hsum8(rs_gt), s_lt = hsum8(rs_lt);
+        if (gt + num_over > 128u) {
+            num_under += lt;
+            mn = guess;
+            guess = __fdiv_rn(s_gt, (float)gt);
+        } else if (lt + num_under > 128u) {
+            num_over += gt;
+            mx = guess;
+            guess = __fdiv_rn(s_lt, (float)lt);
+        } else {
+            break;
+        }
+    }
+    if (threadIdx.x == 0)
+        *out = guess;
 }
 
 }  // namespace
@@ -660,6 +728,13 @@ int launch_cvt_luma8f(const void *pixels, int pixel_format, size_t n_pixels, con
         cvt_luma8f_kernel<YUME_PDQ_CUDA_PIXEL_RGBA8, false><<<grid, 256, 0, s>>>(px, n_pixels, cr, cg, cb, out);
     else
         cvt_luma8f_kernel<YUME_PDQ_CUDA_PIXEL_RGBA8, true><<<grid, 256, 0, s>>>(px, n_pixels, cr, cg, cb, out);
+    YPDQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_avx2_style_threshold(const float *pdqf, float *out, cudaStream_t s)
+{
+    avx2_style_threshold_kernel<<<1, 32, 0, s>>>(pdqf, out);
     YPDQ_LAUNCH_CHECK();
     return 0;
 }

@@ -140,16 +140,19 @@ class ShardedMatcher:
         on_host = not (hasattr(local_frames, "is_cuda") and local_frames.is_cuda)
         if on_host and not hasattr(local_frames, "is_cuda"):
             local_frames = torch.from_numpy(np.ascontiguousarray(local_frames))
-        kern = CudaKernel(self.device)
+        main = torch.cuda.current_stream(dev)
+        # every kernel of this call runs on the caller's current stream (PyTorch side streams do not synchronise
+        # with the legacy default stream, so launching on stream 0 under torch.cuda.stream(...) would race)
+        kern = CudaKernel(self.device, stream=main)
         hashes = hashes_out if hashes_out is not None else torch.empty((n, 8, 32), dtype=torch.uint8, device=dev)
         gath = [torch.empty((W * chunk * 8, 32), dtype=torch.uint8, device=dev) for _ in range(2)]
         out = torch.zeros((cap, 16), dtype=torch.uint8, device=dev)
         cnt = torch.zeros(1, dtype=torch.int32, device=dev)
-        main = torch.cuda.current_stream(dev)
         if on_host:
             copy = torch.cuda.Stream(dev)
             bufs = [torch.empty((chunk,) + tuple(local_frames.shape[1:]), dtype=local_frames.dtype, device=dev)
                     for _ in range(2)]
+            copy.wait_stream(main)     # the staging buffers come from `main`'s allocator pool
             ev_copied = [torch.cuda.Event() for _ in range(2)]
             ev_done = [torch.cuda.Event() for _ in range(2)]
         n_chunks = (n + chunk - 1) // chunk
@@ -173,7 +176,7 @@ class ShardedMatcher:
             g = gath[b][: W * k * 8]
             dist.all_gather_into_tensor(g, hashes[f0:f0 + k].reshape(-1, 32), group=self.group)
             # chunk-local needle index p = r * 8k + i; rebased below to 8 * (r * n + f0) + i
-            self.matcher.find_device(g, W * k * 8, out, cap, cnt, needle_base=c * W * chunk * 8)
+            self.matcher.find_device(g, W * k * 8, out, cap, cnt, needle_base=c * W * chunk * 8, stream=main)
         # every rank must take the same decision about a retry (the retry runs collectives): agree on the
         # largest per-rank match count
         worst = cnt.to(torch.int64)
