@@ -17,10 +17,19 @@ The JSON line also carries the two other figures of BASELINE.json's metric -- th
 its roofline, a CPU baseline (the AVX2 hasher + AVX-512/u64 matcher port of the
 reference, oracle/cpu_baseline.cpp) timed on a bounded sample, the end-to-end number
 through the host-pointer C ABI, clocks sampled during the timed region and the number
-of kernels this library launched.
+of kernels this library launched, and (every N):
+  "parity"   the sharded matcher's merged match list == the CPU oracle's on a
+             sub-sampled problem (200,000 rows x ALL of the job's needles): full
+             equality, (row, needle, distance);
+  "config5"  BASELINE config 5: 125M synthetic rows per GPU (1e9 over 8 GPUs),
+             1024 images x 8 dihedrals per batch matched in ONE 8192-needle launch;
+  "config4"  BASELINE config 4: 65,536 device-generated frames (total) hashed and
+             matched against the sharded 10M-row DB through ShardedMatcher.screen;
+  "scan".sharded_e2e_us (N > 1)  needles on rank 0 -> broadcast -> N shard scans ->
+             merged (OR) result on the host.
 
-Only this file's cpu_baseline / --impl reference legs touch oracle/ (as the measured
-CPU reference); the GPU arm never does.
+Only this file's cpu_baseline / --impl reference / parity legs touch oracle/ (as the
+measured CPU reference and as the checker); the GPU arm's timed regions never do.
 """
 from __future__ import annotations
 
@@ -222,6 +231,24 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+def plant_rows(rng, needles_host, n_plant, row_lo, row_hi, write_row, own_lo=None, own_hi=None, stride=1):
+    """Plants copies of random needles (0..33 bits away) at random rows of [row_lo, row_hi) that are multiples of
+    `stride`; write_row(global_row, bytes32) is called for rows inside [own_lo, own_hi).  Deterministic in rng, so
+    every rank computes the same list.  Returns [(global_row, needle_index, distance)]."""
+    planted = []
+    slots = rng.choice((row_hi - row_lo + stride - 1) // stride, size=n_plant, replace=False)
+    for slot in slots:
+        row = row_lo + int(slot) * stride
+        j = int(rng.integers(0, needles_host.shape[0]))
+        d = int(rng.integers(0, 34))
+        bits = np.unpackbits(needles_host[j].copy())
+        bits[rng.choice(256, size=d, replace=False)] ^= 1
+        if own_lo is None or own_lo <= row < own_hi:
+            write_row(row, np.packbits(bits))
+        planted.append((row, j, d))
+    return planted
+
+
 def main():
     global DB_ROWS, FRAMES_PER_GPU, _REAL_STDOUT
     # Libraries write banners to stdout (NCCL prints "NCCL version ..." at the first collective): keep fd 1 for the
@@ -237,9 +264,13 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=256, help="frames per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison on the sub-sampled problem")
+    ap.add_argument("--no-config4", action="store_true")
+    ap.add_argument("--no-config5", action="store_true")
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help=argparse.SUPPRESS)
-    # BASELINE config 5 (INT/tensor regime): --db-rows 1000000000 --frames 128 on 8 GPUs (1024 images per batch)
     ap.add_argument("--db-rows", type=int, default=DB_ROWS, help=argparse.SUPPRESS)
+    ap.add_argument("--c5-rows-per-gpu", type=int, default=125_000_000, help=argparse.SUPPRESS)
+    ap.add_argument("--c4-frames", type=int, default=65_536, help=argparse.SUPPRESS)
     args = ap.parse_args()
     DB_ROWS, FRAMES_PER_GPU = args.db_rows, args.frames
     if args.warmup < 3 and args.impl == "ours":
@@ -266,6 +297,18 @@ def main():
     n_gpus = world
     B = args.frames
     hbm_peak, peak_src, peaks = measured_peaks()
+    main_stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if n_gpus > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if n_gpus > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # ---- setup (untimed): inputs resident in HBM ----------------------------
     kern = yp.CudaKernel(local_rank)
@@ -282,18 +325,23 @@ def main():
     outs = {"hashes": torch.empty((B, 8, 32), dtype=torch.uint8, device=dev),
             "quality": torch.empty((B, 8), dtype=torch.float32, device=dev),
             "thresholds": torch.empty((B, 8), dtype=torch.float32, device=dev)}
-    q_all = B * 8 * n_gpus
-    needles_all = torch.empty((q_all, 32), dtype=torch.uint8, device=dev)
-    CAP = 1 << 16
-    match_out = torch.zeros((CAP, 16), dtype=torch.uint8, device=dev)
-    match_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
-    gathered = torch.empty((n_gpus, CAP // 16, 16), dtype=torch.uint8, device=dev) if n_gpus > 1 else None
-    gathered_cnt = torch.empty(n_gpus, dtype=torch.int32, device=dev) if n_gpus > 1 else None
+    q_loc = B * 8
+    q_all = q_loc * n_gpus
+    local_needles = outs["hashes"].reshape(-1, 32)
+    needles_all = torch.empty((q_all, 32), dtype=torch.uint8, device=dev) if n_gpus > 1 else local_needles
+    # match list with its count in a header row: ONE all-gather moves both (N > 1)
+    CAP = 1 << 16 if n_gpus == 1 else 1 << 12
+    list_buf = torch.zeros((1 + CAP, 16), dtype=torch.uint8, device=dev)
+    match_cnt = list_buf[0, :4].view(torch.int32)
+    match_out = list_buf[1:]
+    gathered = torch.empty((n_gpus, 1 + CAP, 16), dtype=torch.uint8, device=dev) if n_gpus > 1 else None
+    side = torch.cuda.Stream(dev) if n_gpus > 1 else None
+    ev_hash, ev_gath = torch.cuda.Event(), torch.cuda.Event()
 
     # plant rows so the scan has something to find: copies of this job's own hashes, 0..31 bits away
     kern.hash_batch(frames, out=outs)
     torch.cuda.synchronize()
-    local_hashes = outs["hashes"].reshape(-1, 32).cpu().numpy()
+    local_hashes = local_needles.cpu().numpy()
     rng = np.random.default_rng(1234 + rank)
     planted = []
     for k in range(N_PLANT):
@@ -303,25 +351,30 @@ def main():
         flips = rng.choice(256, size=int(rng.integers(0, 32)), replace=False)
         h[flips] ^= 1
         db.write_rows(lrow, np.packbits(h)[None])
-        planted.append((row0 + lrow, rank * B * 8 + j))
+        planted.append((row0 + lrow, rank * q_loc + j))
 
     def step():
         kern.hash_batch(frames, out=outs)
-        if n_gpus > 1:
-            dist.all_gather_into_tensor(needles_all, outs["hashes"].reshape(-1, 32))
-            nd = needles_all
-        else:
-            nd = outs["hashes"].reshape(-1, 32)
+        if n_gpus == 1:
+            match_cnt.zero_()
+            matcher.find_device(local_needles, q_loc, match_out, CAP, match_cnt, algo=yp.ALGO_AUTO)
+            return
+        # N > 1: the all-gather of the needles runs on a side stream while this rank's OWN needles are matched; the
+        # other ranks' needles follow in (up to) two launches; one all-gather returns count + list of every rank
+        ev_hash.record(main_stream)
+        with torch.cuda.stream(side):
+            side.wait_event(ev_hash)
+            dist.all_gather_into_tensor(needles_all, local_needles)
+            ev_gath.record(side)
         match_cnt.zero_()
-        matcher.find_device(nd, q_all, match_out, CAP, match_cnt, algo=yp.ALGO_AUTO)
-        if n_gpus > 1:   # gather of the (small, fixed-capacity) match lists: the only exchange besides the needles
-            dist.all_gather_into_tensor(gathered_cnt, match_cnt)
-            dist.all_gather_into_tensor(gathered.reshape(-1, 16), match_out[: CAP // 16])
-
-    def barrier():
-        if n_gpus > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        matcher.find_device(local_needles, q_loc, match_out, CAP, match_cnt, needle_base=rank * q_loc)
+        main_stream.wait_event(ev_gath)
+        if rank > 0:
+            matcher.find_device(needles_all[: rank * q_loc], rank * q_loc, match_out, CAP, match_cnt, needle_base=0)
+        if rank < n_gpus - 1:
+            matcher.find_device(needles_all[(rank + 1) * q_loc:], (n_gpus - 1 - rank) * q_loc, match_out, CAP, match_cnt,
+                                needle_base=(rank + 1) * q_loc)
+        dist.all_gather_into_tensor(gathered.reshape(-1, 16), list_buf)
 
     for _ in range(args.warmup):
         step()
@@ -342,22 +395,31 @@ def main():
     elapsed_ms = e0.elapsed_time(e1)
     launches = yp.launch_count() - launches0
     clocks = sampler.stop()
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     lt = torch.tensor([launches], dtype=torch.int64, device=dev)
     if n_gpus > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-    elapsed_ms = float(t.item())
+    elapsed_ms = max_over_ranks(elapsed_ms)
     ms_per_step = elapsed_ms / args.steps
     value = n_gpus * B / (ms_per_step * 1e-3)
 
     # ---- correctness of what was timed (untimed check) -----------------------
     n_matches = int(match_cnt.item())
-    got = match_out[:min(n_matches, CAP)].cpu().numpy().view(yp.MATCH_DTYPE).reshape(-1)
+    if n_matches > CAP:
+        raise SystemExit(f"bench.py: rank {rank}: {n_matches} matches overflow the list capacity {CAP}")
+    got = match_out[:n_matches].cpu().numpy().view(yp.MATCH_DTYPE).reshape(-1)
     got_set = {(int(r), int(n)) for r, n in zip(got["row"], got["needle"])}
     missing = [p for p in planted if p not in got_set]
     if missing:
         raise SystemExit(f"bench.py: rank {rank}: {len(missing)} planted matches were not found")
+    total_matches = n_matches
+    if n_gpus > 1:
+        g = gathered.cpu().numpy()
+        total_matches = int(sum(int(g[r, 0, :4].view(np.int32)[0]) for r in range(n_gpus)))
+
+    # ---- parity: merged multi-GPU match list == CPU oracle on a sub-sampled problem ------
+    parity = None
+    if not args.no_parity:
+        parity = parity_leg(args, yp, sharded, dist, torch, dev, rank, n_gpus, local_rank, local_needles, needles_all, q_all)
 
     # ---- per-kernel timings for the rooflines (CUDA events on the launch stream) ------
     def time_kernel(fn, iters, flush=None):
@@ -380,29 +442,62 @@ def main():
         ts = [a.elapsed_time(b) for a, b in ev]
         return float(np.mean(ts)), float(np.median(ts)), float(np.min(ts))
 
-    # DRAM traffic per launch from the ncu captures under profiles/r01ak/ (bytes read + written), per row / per frame;
+    # DRAM traffic per launch from the ncu captures under profiles/ (bytes read + written), per row / per frame;
     # reported only for the sizes those captures were taken at (one GPU, the default DB, f32 frames)
     default_sizes = n_gpus == 1 and DB_ROWS == (10_000_000 // 2048 + 1) * 2048
     traffic_tensor = (324819200 + 3689984) / 10_000_384 * shard_rows if default_sizes and B == 4096 else None
     traffic_hash = (1235472640 + 4763904) / 1184 * B if default_sizes else None
     traffic_scan = (320080128 + 5022464) / 10_000_384 * shard_rows if default_sizes else None
     line_extra = {}
+    mxf4_peak, mxf4_clk = yp.measure_mxf4_peak(local_rank, 20000)
+    flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
+    nd = local_needles
+    # (1) dominant kernel of the step: large-batch match on the tensor cores
+    m_mean, m_med, _ = time_kernel(
+        lambda: (match_cnt.zero_(), matcher.find_device(nd, q_loc, match_out, CAP, match_cnt)), 3)
+    pairs = shard_rows * q_loc
+    # (2) hash kernel (HBM bound): algorithmic bytes = frames in + hashes/quality/thresholds out
+    h_mean, h_med, h_min = time_kernel(lambda: kern.hash_batch(frames, out=outs), 10, flush)
+    hash_bytes = B * (512 * 512 * 4 + 8 * 32 + 8 * 4 + 8 * 4)
+    # (3) headline scan: 8 needles vs the resident shard (HBM bound), L2 flushed between launches
+    n8 = nd[:8].contiguous()
+    s_mean, s_med, s_min = time_kernel(
+        lambda: matcher.find_device(n8, 8, match_out, CAP, match_cnt), 20, flush)
+    # (3b) the needle counts of the reference's batched CpuMatcher<B, N> and of a 128-frame video chunk
+    batch_us = {}
+    for qb in (32, 128, 1024):
+        if qb <= q_loc:
+            nb = nd[:qb].contiguous()
+            b_mean, _, _ = time_kernel(lambda: matcher.find_device(nb, qb, match_out, CAP, match_cnt), 10, flush)
+            batch_us[str(qb)] = b_mean * 1e3
+    scan_bytes = shard_rows * 32
+    share = m_mean / (m_mean + h_mean)
+    # (3c) N > 1: the sharded 8-needle query end to end (needles on rank 0 -> broadcast -> N shard scans -> OR)
+    sharded_e2e = None
+    if n_gpus > 1:
+        q8 = n8.clone()
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+
+        def sharded_scan():
+            dist.broadcast(q8, src=0)
+            match_cnt.zero_()
+            matcher.find_device(q8, 8, match_out, CAP, match_cnt)
+            flag.copy_(match_cnt.clamp(max=1))
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            return bool(flag.item())     # host-visible answer: includes the synchronisation
+
+        for _ in range(5):
+            sharded_scan()
+        barrier()
+        ts = []
+        for _ in range(30):
+            t0 = time.perf_counter()
+            sharded_scan()
+            ts.append((time.perf_counter() - t0) * 1e6)
+        sharded_e2e = max_over_ranks(float(np.median(ts)))
+    del flush
+
     if rank == 0:
-        flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
-        nd = outs["hashes"].reshape(-1, 32)
-        # (1) dominant kernel of the step: large-batch match on the tensor cores
-        m_mean, m_med, _ = time_kernel(
-            lambda: (match_cnt.zero_(), matcher.find_device(nd, B * 8, match_out, CAP, match_cnt)), 3)
-        pairs = shard_rows * B * 8
-        # (2) hash kernel (HBM bound): algorithmic bytes = frames in + hashes/quality/thresholds out
-        h_mean, h_med, h_min = time_kernel(lambda: kern.hash_batch(frames, out=outs), 10, flush)
-        hash_bytes = B * (512 * 512 * 4 + 8 * 32 + 8 * 4 + 8 * 4)
-        # (3) headline scan: 8 needles vs the resident shard (HBM bound), L2 flushed between launches
-        n8 = nd[:8].contiguous()
-        s_mean, s_med, s_min = time_kernel(
-            lambda: matcher.find_device(n8, 8, match_out, CAP, match_cnt), 20, flush)
-        scan_bytes = shard_rows * 32
-        share = m_mean / (m_mean + h_mean)
         # Tensor roofline.  At threshold <= 36 the matcher runs the 128-bit prefix filter on the tensor cores with two
         # rows per accumulator column (match_tensor4x2_kernel): one (row, needle) pair = 128 multiply-adds = 256 ops of
         # the packed-FP4 MMA (tcgen05.mma kind::mxf4, e2m1 operands, f32 accumulate; in the high field 6 of the 128
@@ -410,28 +505,27 @@ def main():
         # POPC check of the rare candidates.  Above threshold 36 the full 256-bit dot product runs
         # (match_tensor4_kernel), 512 ops.  Peak: MEASURED_PEAKS.json holds a dense bf16 rate but no FP4 one, and 4 x
         # its bf16 figure (FP4 : bf16 = 4 : 1 on the tensor pipe) is BELOW what this kernel achieves (cuBLAS bf16 on
-        # random data is power-limited to ~1.4 GHz, +-1 operands are not), so the denominator is the issue rate of the
-        # very same instruction measured live on this GPU with no loads and no epilogue
+        # random data is power-limited to ~1.4 GHz, +-1 operands are not), so the denominator is SELF-MEASURED: the
+        # issue rate of the very same instruction measured live on this GPU with no loads and no epilogue
         # (yume_pdq_cuda_measure_mxf4_peak); the bf16-derived figure is kept beside it.
         paired = THRESHOLD <= 36
         ops_per_pair = 256 if paired else 512
-        executed_per_pair = 256 if paired else 512
         bf16 = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
-        mxf4_peak, mxf4_clk = yp.measure_mxf4_peak(local_rank, 20000)
         achieved_tops = pairs * ops_per_pair / (m_mean * 1e-3) / 1e12
         line_extra["roofline"] = {
             "kernel": "%s (tcgen05.mma kind::mxf4; needle batch %d x this rank's %d-row shard)"
                       % ("match_tensor4x2_kernel: 128-bit prefix filter, two rows per f32 accumulator" if paired else
-                         "match_tensor4_kernel<256-bit>", B * 8, shard_rows),
+                         "match_tensor4_kernel<256-bit>", q_loc, shard_rows),
             "bound": "tensor", "achieved": achieved_tops, "peak": mxf4_peak, "unit": "TFLOP/s",
             "frac": achieved_tops / mxf4_peak,
-            "peak_source": ("live: back-to-back tcgen05.mma kind::mxf4 M128 N240 K64 on this GPU, %.1f SM clk per MMA "
-                            "(yume_pdq_cuda_measure_mxf4_peak)" % mxf4_clk),
+            "peak_is_self_measured": True,
+            "peak_source": ("SELF-MEASURED (MEASURED_PEAKS.json has no FP4 entry): back-to-back tcgen05.mma kind::mxf4 "
+                            "M128 N240 K64 on this GPU, %.1f SM clk per MMA (yume_pdq_cuda_measure_mxf4_peak)" % mxf4_clk),
             "peak_bf16_x4": 4.0 * bf16, "frac_of_bf16_x4": achieved_tops / (4.0 * bf16),
             "peak_bf16_x4_source": "4 x bf16_tflops_sustained of MEASURED_PEAKS.json" if peaks else
                                    "4 x 1590 (B200_PROFILING.md fallback)",
-            "tensor_ops_per_pair": ops_per_pair, "executed_tensor_ops_per_pair": executed_per_pair,
-            "executed_frac": pairs * executed_per_pair / (m_mean * 1e-3) / 1e12 / mxf4_peak,
+            "tensor_ops_per_pair": ops_per_pair, "executed_tensor_ops_per_pair": ops_per_pair,
+            "executed_frac": achieved_tops / mxf4_peak,
             "tpairs_per_s": pairs / (m_mean * 1e-3) / 1e12,
             "traffic": traffic_tensor, "traffic_source": "profiles/r01ak/traffic_tensor32k.csv (ncu, same sizes)",
             "ms_per_launch": m_mean, "share_of_step": share,
@@ -450,8 +544,18 @@ def main():
             "frac": scan_bytes / (s_mean * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src,
             "rows_per_s": shard_rows / (s_mean * 1e-3), "traffic": traffic_scan, "algorithmic_bytes": scan_bytes,
             "traffic_source": "profiles/r01ak/traffic_scan.csv (ncu, same sizes)",
+            "needle_batches_us": batch_us,
+            "sharded_e2e_us": sharded_e2e,
+            "sharded_e2e_path": None if n_gpus == 1 else
+            "8 needles on rank 0 -> NCCL broadcast -> every rank scans its shard -> NCCL all-reduce(MAX) of the flag -> "
+            "host bool (median wall clock of 30 queries, max over ranks)",
         }
-        del flush
+
+    # ---- BASELINE configs 5 and 4 ---------------------------------------------------
+    c5 = None if args.no_config5 else config5_leg(args, yp, dist, torch, dev, rank, n_gpus, local_rank, frames, mxf4_peak,
+                                                   barrier, max_over_ranks)
+    c4 = None if args.no_config4 else config4_leg(args, yp, sharded, dist, torch, dev, rank, n_gpus, local_rank, sm,
+                                                   barrier, max_over_ranks)
 
     # ---- end to end through the host-pointer C ABI ---------------------------------
     e2e = None
@@ -478,16 +582,13 @@ def main():
         for _ in range(e2e_steps):
             m = e2e_step()
         barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if n_gpus > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+        dt = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": n_gpus * B * e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(B * 512 * 512 * 4),
                "d2h_bytes_per_step": int(B * 8 * 32 + 16 + len(m) * 16) if n_gpus == 1 else
                int(B * 8 * 32 + 4 + (1 << 16) * 16 * n_gpus),
                "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
+               "h2d_gbs_per_rank": B * 512 * 512 * 4 * e2e_steps / dt / 1e9,
                "path": ("yume_pdq_cuda_screen_batch(pinned host frames -> host hashes + sorted host match list)"
                         if n_gpus == 1 else
                         "ShardedMatcher.screen(pinned host frames): chunked H2D || yume_pdq_cuda_hash_batch -> NCCL "
@@ -518,11 +619,7 @@ def main():
         for _ in range(e2e_steps):
             m8 = e2e8_step()
         barrier()
-        dt8 = time.perf_counter() - t0
-        tt = torch.tensor([dt8], dtype=torch.float64, device=dev)
-        if n_gpus > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt8 = float(tt.item())
+        dt8 = max_over_ranks(time.perf_counter() - t0)
         e2e["luma8"] = {"value": n_gpus * B * e2e_steps / dt8, "unit": UNIT,
                         "h2d_bytes_per_step": int(B * 512 * 512), "ms_per_step": dt8 / e2e_steps * 1e3,
                         "d2h_bytes_per_step": int(B * 8 * 32 + 16 + len(m8) * 16) if n_gpus == 1 else
@@ -530,6 +627,19 @@ def main():
                         "path": "the same call with pinned 8-bit luma frames (yume_pdq_cuda_screen_batch_pixels, "
                                 "YUME_PDQ_CUDA_PIXEL_LUMA8): conversion fused into the hash kernel"}
         del host8
+
+        # the reference's single-frame C ABI (what integration/hash.py calls): per-call latency from pageable host memory
+        if rank == 0:
+            one = frames[0].cpu().numpy()
+            for _ in range(5):
+                yp.hash_get_threshold(one)
+            t0 = time.perf_counter()
+            for _ in range(200):
+                yp.hash_get_threshold(one)
+            e2e["single_frame_abi"] = {
+                "us_per_call": (time.perf_counter() - t0) / 200 * 1e6,
+                "path": "yume_pdq_hash_smart_kernel through ctypes: one 1 MiB upload, 4 kernels, one 66 KB download, one sync",
+                "reference_published_us": 81.0, "reference_source": "README.md:170-173 (AVX2 build through ctypes, Ryzen 9 7950X)"}
 
     cpu_bl = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
@@ -542,7 +652,9 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 (hash) / e2m1 x e2m1 -> f32 exact (match, tensor cores) / u32 popcount (8-needle scan)",
             "data": "synthetic", "config": workload_config(n_gpus),
             "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks,
-            "matches_per_step": n_matches, "planted": N_PLANT,
+            "matches_per_step": total_matches, "planted": N_PLANT * n_gpus,
+            "parity_checked": bool(parity and parity.get("checked")), "parity": parity,
+            "config5": c5, "config4": c4,
             "cpu_baseline": cpu_bl,
         }
         line.update(line_extra)
@@ -551,6 +663,219 @@ def main():
     if n_gpus > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+PARITY_ROWS = 200_000
+PARITY_SCALAR_ROWS = 16_384      # rows (every stride-th of the 200,000) the scalar oracle checks, divided by N
+
+
+def parity_leg(args, yp, sharded, dist, torch, dev, rank, n_gpus, local_rank, local_needles, needles_all, q_all):
+    """Full equality of the sharded matcher's merged match list with the CPU oracle, on a sub-sampled problem: a
+    200,000-row synthetic DB (row-range sharded over the N ranks exactly like the timed one) x ALL q_all needles of
+    the job.  Rank 0 compares (row, needle, distance) lists: against the AVX-512 port of the reference matcher on all
+    rows, and against the scalar oracle (oracle/pdq_oracle.c, the pinned one) on every stride-th row, where half of
+    the plants sit.  A mismatch aborts the bench."""
+    if n_gpus > 1:
+        dist.all_gather_into_tensor(needles_all, local_needles)
+    torch.cuda.synchronize()
+    needles_host = needles_all.cpu().numpy()
+    seed = SEED + 1
+    smp = sharded.ShardedMatcher(
+        PARITY_ROWS, THRESHOLD,
+        lambda b, e, d: yp.CudaVectorDatabase(device=d, global_row_offset=b, synthetic_rows=e - b, seed=seed),
+        device=local_rank)
+    n_scalar = max(1024, PARITY_SCALAR_ROWS // n_gpus)
+    stride = PARITY_ROWS // n_scalar
+    rng = np.random.default_rng(99)            # the same plants on every rank
+
+    def write(row, bits32):
+        smp.db.write_rows(row - smp.begin, bits32[None])
+
+    planted = plant_rows(rng, needles_host, 96, 0, PARITY_ROWS, write, smp.begin, smp.end, stride=stride)
+    planted += plant_rows(rng, needles_host, 96, 0, PARITY_ROWS, write, smp.begin, smp.end, stride=1)
+    t0 = time.perf_counter()
+    got = smp.find_all(local_needles, cap=1 << 14)        # all-gather needles -> shard scans -> gather + merge
+    t_gpu = time.perf_counter() - t0
+    smp.close()
+    out = {"checked": False, "rows": PARITY_ROWS, "needles": int(q_all), "threshold": THRESHOLD,
+           "matches": int(len(got)), "planted": len(planted), "sharded_find_all_ms": t_gpu * 1e3}
+    if rank != 0:
+        return out
+    from oracle import pyoracle
+    pyoracle.build()
+    orc = pyoracle.get()
+    rows = orc.synth_db(PARITY_ROWS, 0, seed)
+    rng = np.random.default_rng(99)
+    plant_rows(rng, needles_host, 96, 0, PARITY_ROWS, lambda r, b: rows.__setitem__(r, b), stride=stride)
+    plant_rows(rng, needles_host, 96, 0, PARITY_ROWS, lambda r, b: rows.__setitem__(r, b), stride=1)
+    key = lambda m: [(int(r), int(n), int(d)) for r, n, d in zip(m["row"], m["needle"], m["dist"])]
+    got_k = key(got)
+    cpu = pyoracle.CpuBaseline()
+    t0 = time.perf_counter()
+    want_port = key(cpu.match(rows, needles_host, THRESHOLD, True, cpu.hw_threads))
+    t_port = time.perf_counter() - t0
+    if got_k != want_port:
+        raise SystemExit("bench.py: PARITY FAILURE: sharded match list != AVX-512 port of the reference matcher "
+                         f"({len(got_k)} vs {len(want_port)} matches)")
+    t0 = time.perf_counter()
+    sub = np.ascontiguousarray(rows[::stride][:n_scalar])
+    want_scalar = [(r * stride, n, d) for r, n, d in key(orc.matcher_find(sub, needles_host, THRESHOLD))]
+    t_scalar = time.perf_counter() - t0
+    got_sub = [t for t in got_k if t[0] % stride == 0 and t[0] // stride < n_scalar]
+    if got_sub != want_scalar:
+        raise SystemExit("bench.py: PARITY FAILURE: sharded match list != scalar oracle on the sub-sampled rows "
+                         f"({len(got_sub)} vs {len(want_scalar)} matches)")
+    expect = sum(1 for p in planted if p[2] <= THRESHOLD)
+    out.update(checked=True, expected_from_plants_at_least=expect,
+               oracle=("full equality of (row, needle, dist): AVX-512 port of CpuMatcher::find on all %d rows (%.1f s, %d "
+                       "threads) and scalar oracle on every %d-th row (%d rows, %d matches, %.1f s)"
+                       % (PARITY_ROWS, t_port, cpu.hw_threads, stride, n_scalar, len(want_scalar), t_scalar)))
+    return out
+
+
+def config5_leg(args, yp, dist, torch, dev, rank, n_gpus, local_rank, frames, mxf4_peak, barrier, max_over_ranks):
+    """BASELINE config 5 (INT/tensor regime): a 1e9-row DB over 8 GPUs = 125M synthetic rows (4 GB) per GPU -- at N < 8
+    the DB is proportionally smaller (125M x N rows), so per-GPU work is constant --, batches of 1024 images x 8
+    dihedrals: each rank hashes 1024 / N resident frames, the 8192 needles are all-gathered and matched against the
+    rank's shard in ONE launch."""
+    rows_per_gpu = args.c5_rows_per_gpu
+    imgs = 1024 // n_gpus
+    q_loc, q_all = imgs * 8, 1024 * 8
+    kern = yp.CudaKernel(local_rank)
+    db5 = yp.CudaVectorDatabase(device=local_rank, global_row_offset=rank * rows_per_gpu, synthetic_rows=rows_per_gpu,
+                                seed=SEED + 5)
+    m5 = yp.CudaMatcher(db5, THRESHOLD)
+    fr = frames[:imgs]
+    hashes = torch.empty((imgs, 8, 32), dtype=torch.uint8, device=dev)
+    needles = torch.empty((q_all, 32), dtype=torch.uint8, device=dev) if n_gpus > 1 else hashes.reshape(-1, 32)
+    CAP5 = 1 << 14
+    out = torch.zeros((CAP5, 16), dtype=torch.uint8, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    kern.hash_batch(fr, want_quality=False, want_thresholds=False, out={"hashes": hashes})
+    torch.cuda.synchronize()
+    hh = hashes.reshape(-1, 32).cpu().numpy()
+    rng = np.random.default_rng(555 + rank)
+    planted = plant_rows(rng, hh, 16, 0, rows_per_gpu, lambda r, b: db5.write_rows(r, b[None]))
+    planted = {(rank * rows_per_gpu + r, rank * q_loc + j) for r, j, d in planted if d <= THRESHOLD}
+
+    def hash_():
+        kern.hash_batch(fr, want_quality=False, want_thresholds=False, out={"hashes": hashes})
+
+    def gather_():
+        if n_gpus > 1:
+            dist.all_gather_into_tensor(needles, hashes.reshape(-1, 32))
+
+    def match_():
+        cnt.zero_()
+        m5.find_device(needles, q_all, out, CAP5, cnt)
+
+    def step():
+        hash_()
+        gather_()
+        match_()
+
+    def timed(fn, reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b) / reps)
+
+    for _ in range(3):
+        step()
+    steps = 5
+    ms = timed(step, steps)
+    ms_hash, ms_gather, ms_match = timed(hash_, 5), timed(gather_, 5), timed(match_, 3)
+    n = int(cnt.item())
+    got = out[:min(n, CAP5)].cpu().numpy().view(yp.MATCH_DTYPE).reshape(-1)
+    got_set = {(int(r), int(j)) for r, j in zip(got["row"], got["needle"])}
+    if not planted <= got_set:
+        raise SystemExit(f"bench.py: config5: rank {rank}: planted matches missing")
+    db5.close()
+    pairs_gpu = rows_per_gpu * q_all
+    ach = pairs_gpu * 256 / (ms_match * 1e-3) / 1e12
+    return {
+        "workload": "%d synthetic rows per GPU (%d total, %.1f GB per shard), 1024 images x 8 dihedrals per batch, ONE "
+                    "%d-needle launch per batch, threshold %d" % (rows_per_gpu, rows_per_gpu * n_gpus, rows_per_gpu * 32 / 1e9,
+                                                                  q_all, THRESHOLD),
+        "rows_per_gpu": rows_per_gpu, "db_rows_total": rows_per_gpu * n_gpus, "needles_per_batch": q_all,
+        "ms_per_batch": ms, "steps": steps, "batches_per_s": 1e3 / ms, "images_per_s": 1024 / (ms * 1e-3),
+        "tpairs_per_s_total": pairs_gpu * n_gpus / (ms * 1e-3) / 1e12, "tpairs_per_s_per_gpu": pairs_gpu / (ms * 1e-3) / 1e12,
+        "split_ms": {"hash": ms_hash, "all_gather": ms_gather, "match": ms_match},
+        "launches_per_batch": "1 hash + 1 needle expansion + 1 match + 1 candidate verification",
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": mxf4_peak, "unit": "TFLOP/s", "frac": ach / mxf4_peak,
+                     "peak_is_self_measured": True, "tensor_ops_per_pair": 256, "ms_per_launch": ms_match,
+                     "share_of_step": ms_match / ms},
+        "matches_per_batch": n, "planted_found": len(planted), "scaling": "weak (rows per GPU fixed)",
+    }
+
+
+def config4_leg(args, yp, sharded, dist, torch, dev, rank, n_gpus, local_rank, sm, barrier, max_over_ranks):
+    """BASELINE config 4 (video screening): 65,536 device-generated 512x512 f32 frames in total, hashed and matched
+    against the 10M-row DB sharded over the N ranks, through ShardedMatcher.screen (chunked hash -> NCCL all-gather of
+    the chunk's needles -> match against the shard, then gather + merge of the match lists)."""
+    total = args.c4_frames
+    F = total // n_gpus
+    frames4 = torch.empty((F, 512, 512), dtype=torch.float32, device=dev)
+    yp.synth_frames(frames4, F, first_frame=10_000_000 + rank * F, seed=SEED, kind=1, device=local_rank)
+    hashes4 = torch.empty((F, 8, 32), dtype=torch.uint8, device=dev)
+    chunk = 2048
+    kern = yp.CudaKernel(local_rank)
+    kern.hash_batch(frames4, want_quality=False, want_thresholds=False, out={"hashes": hashes4})
+    torch.cuda.synchronize()
+    hh = hashes4.reshape(-1, 32).cpu().numpy()
+    rng = np.random.default_rng(444 + rank)
+    shard_rows = sm.end - sm.begin
+    planted = plant_rows(rng, hh, 16, 0, shard_rows, lambda r, b: sm.db.write_rows(r, b[None]))
+    planted = {(sm.begin + r, rank * F * 8 + j) for r, j, d in planted if d <= THRESHOLD}
+
+    def run():
+        return sm.screen(frames4, hashes_out=hashes4, cap=1 << 14, chunk=chunk)
+
+    run()
+    barrier()
+    reps = 2
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        m = run()
+    barrier()
+    dt = max_over_ranks((time.perf_counter() - t0) / reps)
+    got_set = {(int(r), int(j)) for r, j in zip(m["row"], m["needle"])}
+    if not planted <= got_set:
+        raise SystemExit(f"bench.py: config4: rank {rank}: planted matches missing")
+
+    def timed(fn, reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        barrier()
+        return max_over_ranks(a.elapsed_time(b) / reps)
+
+    ms_hash = timed(lambda: kern.hash_batch(frames4, want_quality=False, want_thresholds=False, out={"hashes": hashes4}), 2)
+    all_needles = torch.empty((total * 8, 32), dtype=torch.uint8, device=dev) if n_gpus > 1 else hashes4.reshape(-1, 32)
+    ms_gather = timed(lambda: dist.all_gather_into_tensor(all_needles, hashes4.reshape(-1, 32)), 2) if n_gpus > 1 else 0.0
+    out = torch.zeros((1 << 14, 16), dtype=torch.uint8, device=dev)
+    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    ms_match = timed(lambda: (cnt.zero_(), sm.matcher.find_device(all_needles, total * 8, out, 1 << 14, cnt)), 2)
+    del frames4
+    pairs_gpu = shard_rows * total * 8
+    return {
+        "workload": "%d device-generated 512x512 f32 frames in total (%d per GPU), 8 dihedral hashes each, matched vs the "
+                    "%d-row DB sharded over %d GPU(s), threshold %d" % (total, F, DB_ROWS, n_gpus, THRESHOLD),
+        "frames_total": total, "frames_per_gpu": F, "needles_total": total * 8, "chunk_frames": chunk if n_gpus > 1 else F,
+        "ms_per_pass": dt * 1e3, "images_per_s": total / dt, "passes": reps,
+        "tpairs_per_s_total": pairs_gpu * n_gpus / dt / 1e12,
+        "path": "ShardedMatcher.screen (wall clock incl. the host-side gather + merge of the match lists)",
+        "split_ms": {"hash_all_frames": ms_hash, "all_gather_all_needles": ms_gather, "match_all_needles_one_launch": ms_match,
+                     "remainder_pipeline_gather_merge": dt * 1e3 - ms_hash - ms_gather - ms_match},
+        "matches": int(len(m)), "planted_found": len(planted),
+    }
 
 
 if __name__ == "__main__":
