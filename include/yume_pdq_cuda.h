@@ -161,7 +161,9 @@ int yume_pdq_cuda_db_destroy(YumePDQ_CudaDb *db);
 size_t yume_pdq_cuda_db_len(const YumePDQ_CudaDb *db);
 int yume_pdq_cuda_db_device(const YumePDQ_CudaDb *db);
 /* device pointer of the resident rows (n_rows x 32 bytes, AoS) */
-const uint8_t *yume_pdq_cuda_db_rows(const YumePDQ_CudaDb *db);
+/* Device pointers to the two planes the haystack is stored as: prefix[r] = bytes 0..15 of row r, suffix[r] = bytes
+ * 16..31 (n_rows x 16 B each).  Prefix filters stream the first plane only. */
+int yume_pdq_cuda_db_planes(const YumePDQ_CudaDb *db, const uint8_t **prefix, const uint8_t **suffix);
 /* overwrite rows [first, first+n) (host or device source) -- used by tests to plant */
 int yume_pdq_cuda_db_write_rows(YumePDQ_CudaDb *db, size_t first_local_row, const uint8_t *rows,
                                 size_t n);
@@ -170,8 +172,8 @@ int yume_pdq_cuda_db_write_rows(YumePDQ_CudaDb *db, size_t first_local_row, cons
 #define YUME_PDQ_CUDA_ALGO_AUTO 0
 #define YUME_PDQ_CUDA_ALGO_EXACT 1   /* unfiltered: 8 POPC per (row, needle) pair */
 #define YUME_PDQ_CUDA_ALGO_TILED 2   /* rows in registers x needles in smem, 96-bit carry-save prefilter */
-#define YUME_PDQ_CUDA_ALGO_STREAM 3  /* TMA bulk-copy ring + prefilter, needle prefixes in registers (q <= 32) */
-#define YUME_PDQ_CUDA_ALGO_TENSOR 4  /* tcgen05.mma kind::mxf4 on +-1.0 e2m1 expanded bits: large needle batches. thresholds <= 36: 128-bit prefix filter on the tensor cores, two rows per accumulator (ALGO_TENSOR_PAIRED) + exact POPC check of the candidates; <= 127: full 256-bit dot products; > 127: kind::i8 */
+/* 3 was a TMA-ring variant of ALGO_TILED (slower; removed) */
+#define YUME_PDQ_CUDA_ALGO_TENSOR 4  /* tcgen05.mma kind::mxf4 on e2m1 operands: needle batches from 14 needles on. thresholds <= 36: 128-bit prefix filter on the tensor cores, two rows per accumulator (ALGO_TENSOR_PAIRED) + exact POPC check of the candidates; <= 127: full 256-bit dot products; > 127: kind::i8 */
 #define YUME_PDQ_CUDA_ALGO_TENSOR_I8 5  /* tcgen05.mma kind::i8 on +-1 int8 expanded bits, any threshold */
 #define YUME_PDQ_CUDA_ALGO_TENSOR_FULL 6    /* kind::mxf4, always the full 256-bit dot product (threshold <= 127) */
 #define YUME_PDQ_CUDA_ALGO_TENSOR_PREFIX 7  /* kind::mxf4, always the 128-bit prefix filter (threshold <= 63) */

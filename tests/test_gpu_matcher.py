@@ -38,7 +38,7 @@ def test_planted_vs_oracle_all_algos(cuda, oracle, n_rows, q):
     assert match_tuples(m.find_all(needles)) == want          # sorted (row, needle) like CpuMatcher::find
     assert m.scan(needles) == (len(want) > 0)
     assert m.find_min(needles) == oracle.matcher_find_min(rows, needles, 31)
-    for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_STREAM, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8,
+    for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8,
                  cuda.ALGO_TENSOR_FULL, cuda.ALGO_TENSOR_PREFIX, cuda.ALGO_TENSOR_PAIRED):
         assert _find_device(cuda, m, needles, algo) == sorted(want), algo
     db.close()
@@ -60,7 +60,7 @@ def test_thresholds(cuda, oracle, threshold):
         got = m.find_all(needles, cap=1 << 18)
         assert len(got) == len(want) and match_tuples(got[:1000]) == want[:1000]
     if threshold <= 40:
-        for algo in (cuda.ALGO_TILED, cuda.ALGO_STREAM):
+        for algo in (cuda.ALGO_TILED,):
             assert _find_device(cuda, m, needles, algo, cap=1 << 18) == sorted(want)
     if len(want) < 200_000:     # the tensor-core paths are exact for every threshold they accept
         assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR, cap=1 << 18) == sorted(want)
@@ -317,8 +317,6 @@ def test_adversarial_dense_matches(cuda, oracle):
     for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8, cuda.ALGO_TENSOR_FULL,
                  cuda.ALGO_TENSOR_PREFIX, cuda.ALGO_TENSOR_PAIRED):
         assert _find_device(cuda, m, needles, algo, cap=1 << 19) == sorted(want)
-    assert _find_device(cuda, m, needles[:32], cuda.ALGO_STREAM, cap=1 << 19) == sorted(
-        t for t in want if t[1] < 32)
     # capacity error contract of the C ABI: first `cap` entries in sorted order + total
     import ctypes as C
     out = np.zeros(10, dtype=cuda.MATCH_DTYPE)
@@ -379,7 +377,7 @@ def test_headline_config_10m(cuda, oracle):
     want = sorted(p for p in planted if p[2] <= 31)
     assert match_tuples(m.find_all(needles)) == want
     assert m.find_min(needles) == (want[0][0], want[0][1])
-    for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_STREAM, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8,
+    for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8,
                  cuda.ALGO_TENSOR_FULL, cuda.ALGO_TENSOR_PREFIX, cuda.ALGO_TENSOR_PAIRED):
         assert _find_device(cuda, m, needles, algo) == want
     # last rows of the last chunk are planted too (tail handling)

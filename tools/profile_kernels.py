@@ -36,7 +36,7 @@ if {"scan", "stream", "tiled", "exact", "tensor", "tensor128", "tensor32k"} & se
         if "scan" in what:
             m.find_device(n8, 8, out, 1 << 16, cnt, algo=yp.ALGO_TILED)
         if "stream" in what:
-            m.find_device(n8, 8, out, 1 << 16, cnt, algo=yp.ALGO_STREAM)
+            m.find_device(n8, 8, out, 1 << 16, cnt, algo=yp.ALGO_TILED)
         if "exact" in what:
             m.find_device(n8, 8, out, 1 << 16, cnt, algo=yp.ALGO_EXACT)
         if "tiled" in what:

@@ -43,25 +43,11 @@ def main():
         cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
         for q in (8, 16, 32):
             needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
-            for name, algo in (("exact", yp.ALGO_EXACT), ("tiled", yp.ALGO_TILED), ("stream", yp.ALGO_STREAM)):
+            for name, algo in (("exact", yp.ALGO_EXACT), ("tiled", yp.ALGO_TILED)):
                 med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 16, cnt, algo=algo), flush=flush)
                 print(f"scan 10M x {q:3d} {name:7s}: median {med:8.1f} us  best {best:8.1f} us  "
                       f"{n * 32 / med / 1e3:7.1f} GB/s  {n * q / med / 1e6:8.3f} Tpairs/s  hits={int(cnt.item())}")
                 cnt.zero_()
-        db.close()
-    if "scanv" in what:   # tiled-kernel variants (YPDQ_TILED_VARIANT, one process per variant)
-        n = (10_000_000 // 2048 + 1) * 2048
-        db = yp.CudaVectorDatabase(synthetic_rows=n)
-        m = yp.CudaMatcher(db, 31)
-        out = torch.zeros((1 << 16, 16), dtype=torch.uint8, device="cuda")
-        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
-        for q in (8, 16, 64, 256):
-            needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
-            med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 16, cnt, algo=yp.ALGO_TILED), flush=flush)
-            med2, best2 = timeit(lambda: m.find_device(needles, q, out, 1 << 16, cnt, algo=yp.ALGO_TILED), flush=None)
-            print(f"variant {os.environ.get('YPDQ_TILED_VARIANT', '-')}: scan 10M x {q:3d}: median {med:8.1f} us  "
-                  f"best {best:8.1f} us  {n * 32 / med / 1e3:7.1f} GB/s  {n * q / med / 1e6:8.3f} Tpairs/s   "
-                  f"[back-to-back, no flush: median {med2:8.1f} us best {best2:8.1f}]")
         db.close()
     if "tc4v" in what:   # packed-FP4 tensor matcher variants (YPDQ_TC4_VARIANT, one process per variant)
         n = (10_000_000 // 2048 + 1) * 2048

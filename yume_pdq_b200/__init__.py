@@ -28,7 +28,7 @@ LIB_PATH = os.environ.get("YUME_PDQ_CUDA_LIB") or os.path.join(HERE, "libyume_pd
 
 MATCH_DTYPE = np.dtype([("row", "<u8"), ("needle", "<u4"), ("dist", "<u4")])
 
-ALGO_AUTO, ALGO_EXACT, ALGO_TILED, ALGO_STREAM, ALGO_TENSOR, ALGO_TENSOR_I8 = 0, 1, 2, 3, 4, 5
+ALGO_AUTO, ALGO_EXACT, ALGO_TILED, ALGO_TENSOR, ALGO_TENSOR_I8 = 0, 1, 2, 4, 5
 ALGO_TENSOR_FULL, ALGO_TENSOR_PREFIX, ALGO_TENSOR_PAIRED = 6, 7, 8
 
 OP_T = 0
@@ -97,7 +97,7 @@ SIGNATURES = {
     "yume_pdq_cuda_db_destroy": (C.c_int, [_vp]),
     "yume_pdq_cuda_db_len": (C.c_size_t, [_vp]),
     "yume_pdq_cuda_db_device": (C.c_int, [_vp]),
-    "yume_pdq_cuda_db_rows": (_vp, [_vp]),
+    "yume_pdq_cuda_db_planes": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "yume_pdq_cuda_db_write_rows": (C.c_int, [_vp, C.c_size_t, _vp, C.c_size_t]),
     "yume_pdq_cuda_matcher_scan": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, C.POINTER(C.c_int), _vp]),
     "yume_pdq_cuda_matcher_find": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _vp, C.c_size_t,
@@ -437,8 +437,11 @@ class CudaVectorDatabase:
         return int(lib.yume_pdq_cuda_db_len(self._h))
 
     @property
-    def rows_ptr(self) -> int:
-        return int(lib.yume_pdq_cuda_db_rows(self._h) or 0)
+    def planes_ptr(self) -> tuple[int, int]:
+        """Device addresses of the prefix plane (bytes 0..15 of every row) and the suffix plane (bytes 16..31)."""
+        pre, suf = _vp(), _vp()
+        _check(lib.yume_pdq_cuda_db_planes(self._h, C.byref(pre), C.byref(suf)), "db_planes")
+        return int(pre.value or 0), int(suf.value or 0)
 
     def write_rows(self, first_local_row: int, rows):
         if isinstance(rows, np.ndarray):

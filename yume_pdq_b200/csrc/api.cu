@@ -256,8 +256,12 @@ using namespace ypdq;
 struct YumePDQ_CudaDb {
     int device = 0;
     int sm_count = 148;
-    uint8_t *rows = nullptr;
+    uint8_t *rows = nullptr;     // ONE allocation holding the two planes: n_rows x 16 B prefixes, then n_rows x 16 B suffixes
     size_t n_rows = 0;
+    ypdq::DbPlanes planes() const
+    {
+        return {reinterpret_cast<const uint4 *>(rows), reinterpret_cast<const uint4 *>(rows) + n_rows};
+    }
     uint64_t offset = 0;
     // per-handle scratch for the host-facing calls
     uint8_t *d_needles = nullptr;
@@ -266,7 +270,8 @@ struct YumePDQ_CudaDb {
     size_t out_cap = 0;
     uint32_t *d_count = nullptr;           // [0] count, then 8-byte aligned min key at +8
     unsigned long long *d_min = nullptr;
-    void *h_pin = nullptr;                 // 16 bytes pinned: count + min key
+    void *h_pin = nullptr;                 // pinned: 16 bytes count + min key, then the MatchStats of ALGO_AUTO
+    ypdq::MatchStats *stats = nullptr;
     std::mutex mu;
 };
 
@@ -752,14 +757,29 @@ static int db_alloc(int device, size_t n_rows, uint64_t offset, YumePDQ_CudaDb *
     if (e == cudaSuccess)
         e = cudaMalloc(&db->d_count, 16);
     if (e == cudaSuccess)
-        e = cudaMallocHost(&db->h_pin, 16);
+        e = cudaMallocHost(&db->h_pin, 64);
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         yume_pdq_cuda_db_destroy(db);
         return e == cudaErrorMemoryAllocation ? YUME_PDQ_CUDA_E_NOMEM : (int)e;
     }
     db->d_min = reinterpret_cast<unsigned long long *>(db->d_count + 2);
+    db->stats = new (static_cast<uint8_t *>(db->h_pin) + 16) ypdq::MatchStats();
     *out = db;
+    return 0;
+}
+
+// rows (n x 32 B, host or device) -> the two planes of `db`, starting at row `first`
+static int split_rows(YumePDQ_CudaDb *db, size_t first, const uint8_t *rows, size_t n)
+{
+    if (n == 0)
+        return 0;
+    uint8_t *pre = db->rows + first * 16, *suf = db->rows + (db->n_rows + first) * 16;
+    for (size_t r0 = 0; r0 < n; r0 += (size_t)16 << 20) {      // strided copies of at most 16M rows each
+        const size_t cnt = std::min<size_t>((size_t)16 << 20, n - r0);
+        YPDQ_CUDA_TRY(cudaMemcpy2D(pre + r0 * 16, 16, rows + r0 * 32, 32, 16, cnt, cudaMemcpyDefault));
+        YPDQ_CUDA_TRY(cudaMemcpy2D(suf + r0 * 16, 16, rows + r0 * 32 + 16, 32, 16, cnt, cudaMemcpyDefault));
+    }
     return 0;
 }
 
@@ -771,16 +791,12 @@ int yume_pdq_cuda_db_create(int device, const uint8_t *rows, size_t n_rows, uint
     int rc = db_alloc(device, n_rows, global_row_offset, out);
     if (rc)
         return rc;
-    if (n_rows) {
-        cudaError_t e = cudaMemcpy((*out)->rows, rows, n_rows * 32, cudaMemcpyDefault);
-        if (e != cudaSuccess) {
-            (void)cudaGetLastError();
-            yume_pdq_cuda_db_destroy(*out);
-            *out = nullptr;
-            return (int)e;
-        }
+    rc = split_rows(*out, 0, rows, n_rows);
+    if (rc) {
+        yume_pdq_cuda_db_destroy(*out);
+        *out = nullptr;
     }
-    return 0;
+    return rc;
 }
 
 int yume_pdq_cuda_db_create_synthetic(int device, size_t n_rows, uint64_t global_row_offset, uint64_t seed,
@@ -789,11 +805,25 @@ int yume_pdq_cuda_db_create_synthetic(int device, size_t n_rows, uint64_t global
     int rc = db_alloc(device, n_rows, global_row_offset, out);
     if (rc)
         return rc;
-    rc = launch_synth_rows((*out)->rows, n_rows, global_row_offset, seed, nullptr);
+    // generated in chunks of 32-byte rows (the generator is shared with yume_pdq_cuda_synth_rows), then split
+    const size_t chunk = std::min<size_t>(n_rows, (size_t)8 << 20);
+    uint8_t *tmp = nullptr;
+    if (chunk && cudaMalloc(&tmp, chunk * 32) != cudaSuccess) {
+        (void)cudaGetLastError();
+        rc = YUME_PDQ_CUDA_E_NOMEM;
+    }
+    for (size_t r0 = 0; rc == 0 && r0 < n_rows; r0 += chunk) {
+        const size_t cnt = std::min(chunk, n_rows - r0);
+        rc = launch_synth_rows(tmp, cnt, global_row_offset + r0, seed, nullptr);
+        if (rc == 0)
+            rc = split_rows(*out, r0, tmp, cnt);
+    }
     if (rc == 0) {
         cudaError_t e = cudaDeviceSynchronize();
         rc = e == cudaSuccess ? 0 : (int)e;
     }
+    if (tmp)
+        cudaFree(tmp);
     if (rc) {
         yume_pdq_cuda_db_destroy(*out);
         *out = nullptr;
@@ -818,7 +848,14 @@ int yume_pdq_cuda_db_destroy(YumePDQ_CudaDb *db)
 
 size_t yume_pdq_cuda_db_len(const YumePDQ_CudaDb *db) { return db ? db->n_rows : 0; }
 int yume_pdq_cuda_db_device(const YumePDQ_CudaDb *db) { return db ? db->device : -1; }
-const uint8_t *yume_pdq_cuda_db_rows(const YumePDQ_CudaDb *db) { return db ? db->rows : nullptr; }
+int yume_pdq_cuda_db_planes(const YumePDQ_CudaDb *db, const uint8_t **prefix, const uint8_t **suffix)
+{
+    if (!db || !prefix || !suffix)
+        return YUME_PDQ_CUDA_E_INVALID;
+    *prefix = db->rows;
+    *suffix = db->rows + db->n_rows * 16;
+    return 0;
+}
 
 int yume_pdq_cuda_db_write_rows(YumePDQ_CudaDb *db, size_t first, const uint8_t *rows, size_t n)
 {
@@ -827,9 +864,7 @@ int yume_pdq_cuda_db_write_rows(YumePDQ_CudaDb *db, size_t first, const uint8_t 
     int rc = ensure_device(db->device);
     if (rc)
         return rc;
-    if (n)
-        YPDQ_CUDA_TRY(cudaMemcpy(db->rows + first * 32, rows, n * 32, cudaMemcpyDefault));
-    return 0;
+    return split_rows(db, first, rows, n);
 }
 
 // shared host-facing driver: mode LIST (hits copied back + sorted) or MIN
@@ -875,9 +910,9 @@ static int match_host(YumePDQ_CudaDb *db, const uint8_t *needles, size_t q, uint
         } init = {0, 0, ~0ull};
         std::memcpy(db->h_pin, &init, 16);
         YPDQ_CUDA_TRY(cudaMemcpyAsync(db->d_count, db->h_pin, 16, cudaMemcpyHostToDevice, s));
-        rc = launch_match(db->rows, db->n_rows, db->offset, d_needles, q, threshold, db->d_out,
+        rc = launch_match(db->planes(), db->n_rows, db->offset, d_needles, q, threshold, db->d_out,
                           mode == MODE_LIST ? dev_cap : 0, db->d_count, db->d_min, mode,
-                          YUME_PDQ_CUDA_ALGO_AUTO, db->sm_count, s);
+                          YUME_PDQ_CUDA_ALGO_AUTO, db->sm_count, s, 0, db->stats);
         if (rc)
             return rc;
         YPDQ_CUDA_TRY(cudaMemcpyAsync(db->h_pin, db->d_count, 16, cudaMemcpyDeviceToHost, s));
@@ -966,8 +1001,8 @@ int yume_pdq_cuda_matcher_find_device(YumePDQ_CudaDb *db, const uint8_t *needles
     int rc = ensure_device(db->device);
     if (rc)
         return rc;
-    return launch_match(db->rows, db->n_rows, db->offset, needles_dev, q, threshold, out_dev, cap,
-                        count_dev, nullptr, MODE_LIST, algo, db->sm_count, (cudaStream_t)stream);
+    return launch_match(db->planes(), db->n_rows, db->offset, needles_dev, q, threshold, out_dev, cap,
+                        count_dev, nullptr, MODE_LIST, algo, db->sm_count, (cudaStream_t)stream, 0, db->stats);
 }
 
 int yume_pdq_cuda_matcher_find_device_base(YumePDQ_CudaDb *db, const uint8_t *needles_dev, size_t q,
@@ -979,8 +1014,8 @@ int yume_pdq_cuda_matcher_find_device_base(YumePDQ_CudaDb *db, const uint8_t *ne
     int rc = ensure_device(db->device);
     if (rc)
         return rc;
-    return launch_match(db->rows, db->n_rows, db->offset, needles_dev, q, threshold, out_dev, cap,
-                        count_dev, nullptr, MODE_LIST, algo, db->sm_count, (cudaStream_t)stream, needle_base);
+    return launch_match(db->planes(), db->n_rows, db->offset, needles_dev, q, threshold, out_dev, cap,
+                        count_dev, nullptr, MODE_LIST, algo, db->sm_count, (cudaStream_t)stream, needle_base, db->stats);
 }
 
 int yume_pdq_cuda_screen_batch(YumePDQ_CudaDb *db, const float *frames, size_t n, uint32_t threshold,
@@ -1049,9 +1084,9 @@ int yume_pdq_cuda_screen_batch_pixels(YumePDQ_CudaDb *db, const void *frames, in
         std::memcpy(db->h_pin, &init, 16);
         YPDQ_CUDA_TRY(cudaMemcpyAsync(db->d_count, db->h_pin, 16, cudaMemcpyHostToDevice, s));
         auto match_chunk = [&](size_t f0, size_t cnt) -> int {
-            return launch_match(db->rows, db->n_rows, db->offset, d_hashes + f0 * 256, cnt * 8, threshold, db->d_out,
+            return launch_match(db->planes(), db->n_rows, db->offset, d_hashes + f0 * 256, cnt * 8, threshold, db->d_out,
                                 dev_cap, db->d_count, db->d_min, MODE_LIST, YUME_PDQ_CUDA_ALGO_AUTO, db->sm_count, s,
-                                (uint32_t)(f0 * 8));
+                                (uint32_t)(f0 * 8), db->stats);
         };
         if (attempt == 0) {
             // pipeline: [H2D chunk i+1] || [hash chunk i -> match chunk i's 8 * cnt needles]

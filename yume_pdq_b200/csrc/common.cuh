@@ -70,6 +70,30 @@ int launch_transform(float *pdqf, size_t n, int op, cudaStream_t s);
 int launch_dihedrals(const float *pdqf, const float *thr0, size_t n, uint8_t *hashes, float *quality,
                      float *thresholds, cudaStream_t s);
 
+// The haystack in HBM: two planes of 16 bytes per row -- pre[r] = bytes 0..15 of row r (what every prefix filter
+// streams), suf[r] = bytes 16..31 (touched only to verify the rare survivors, or by the unfiltered kernels).  A scan
+// that is decided by the prefix moves N x 16 B instead of the N x 32 B an array of 32-byte rows would cost (a 16-byte
+// load from a 32-byte row still drags the whole DRAM sector along).
+struct DbPlanes {
+    const uint4 *pre;
+    const uint4 *suf;
+};
+
+// What the prefix-filter matcher observed on a haystack: written by the device (pinned, mapped memory) at the end
+// of a paired-tensor launch, read by the host when it picks the kernel for the NEXT launch on the same haystack.
+// Random rows pass the 128/122-bit prefix filter at 2e-8 of the pairs (threshold 31); a database of near-duplicate
+// families matched against a video's near-identical frames passes 1e-5 and more, and every candidate costs the
+// paired kernel ~13 ns -- past 2.3e-6 the unfiltered 256-bit tensor kernel (14.8e12 pairs/s) is faster.
+struct MatchStats {
+    // device-written (one launch at a time per haystack: the host-facing calls hold the handle's mutex)
+    volatile unsigned long long candidates;
+    volatile unsigned long long pairs;
+    // host-only: adaptive state of ALGO_AUTO
+    uint32_t fallback_left;      // launches to run unfiltered before the filter is probed again
+    uint32_t fallback_interval;  // doubles while the probes keep finding a dense haystack (8 .. 256)
+};
+constexpr double kPrefixFilterBreakEven = 2.3e-6;   // candidates per pair
+
 enum MatchMode : int { MODE_LIST = 0, MODE_MIN = 1 };
 
 // The match counter of the C ABI is 32 bits wide.  Reserving slots must never wrap it (32768 needles x 10M rows at a
@@ -86,24 +110,24 @@ __device__ __forceinline__ uint32_t reserve_matches(uint32_t *count, uint32_t n)
     return pos;
 }
 #endif
-int launch_match(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
+int launch_match(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
                  size_t q, uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
                  unsigned long long *min_key, int mode, int algo, int sm_count, cudaStream_t s,
-                 uint32_t needle_base = 0);
+                 uint32_t needle_base = 0, MatchStats *stats = nullptr);
 
-int launch_match_tensor(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
+int launch_match_tensor(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
                         size_t q, uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
                         unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base = 0);
 
-int launch_match_tensor4(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
+int launch_match_tensor4(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
                          size_t q, uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
                          unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base = 0,
                          int prefix = -1);
 
-int launch_match_tensor4x2(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
+int launch_match_tensor4x2(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
                            size_t q, uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
                            unsigned long long *min_key, int mode, int sm_count, cudaStream_t s,
-                           uint32_t needle_base = 0);
+                           uint32_t needle_base = 0, MatchStats *stats = nullptr);
 
 int launch_synth_frames(float *frames, size_t n, uint64_t first, uint64_t seed, int kind,
                         cudaStream_t s);

@@ -17,19 +17,16 @@
 //    prefix distance is <= threshold; survivors (3.4e-4 of random pairs at
 //    threshold 31) get the full 8-word distance.  Speed is data dependent,
 //    the match set is not.
-//  * ALGO_STREAM: persistent CTAs, one per SM; a producer lane streams the AoS
-//    database through an 8-stage ring of 16 KB shared-memory buffers with TMA
-//    bulk copies (cp.async.bulk + mbarrier complete_tx); 16 consumer warps take
-//    one row per lane per stage; the needle prefixes stay in registers.
-//  * ALGO_TILED: rows in registers (8 per thread) x needles in shared memory
-//    (2048 per CTA): the INT-pipe-bound regime for large needle batches; also
-//    serves small batches with plain vectorised loads.
+//  * The database lies in HBM as TWO PLANES (DbPlanes, common.cuh): bytes 0..15 of
+//    every row contiguously, then bytes 16..31.  The prefix filter reads the first
+//    plane only -- 16 B per row, fully coalesced -- so a scan moves half the bytes
+//    of the database; only the rare survivors touch the second plane.
+//  * ALGO_TILED: rows in registers (4 per thread) x needles in shared memory
+//    (2048 per CTA): the XU(POPC)-bound small-batch scan.
 //  * ALGO_EXACT: unfiltered 8-POPC kernel (any threshold; the honest baseline).
 //  * Hits are compacted with a warp ballot + one atomicAdd per warp.
 #include <cuda_runtime.h>
 #include <stdint.h>
-
-#include <cstdlib>
 
 #include "common.cuh"
 
@@ -133,7 +130,7 @@ constexpr int EX_ROWS = 4;       // rows per thread
 constexpr int EX_NCHUNK = 1024;  // needles per CTA (32 KB of shared memory)
 
 __global__ void __launch_bounds__(EX_THREADS)
-match_exact_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint4 *__restrict__ needles,
+match_exact_kernel(DbPlanes rows, uint64_t n_rows, const uint4 *__restrict__ needles,
                    uint32_t q, uint32_t thr, Sink sink)
 {
     __shared__ uint4 sn[EX_NCHUNK * 2];
@@ -148,8 +145,8 @@ match_exact_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint4 
     for (int u = 0; u < EX_ROWS; u++) {
         ridx[u] = tile + (uint64_t)u * EX_THREADS + threadIdx.x;
         uint64_t r = ridx[u] < n_rows ? ridx[u] : 0;
-        lo[u] = __ldg(rows + 2 * r);
-        hi[u] = __ldg(rows + 2 * r + 1);
+        lo[u] = __ldg(rows.pre + r);
+        hi[u] = __ldg(rows.suf + r);
     }
     __syncthreads();
     for (uint32_t i = 0; i < nc; i++) {
@@ -168,11 +165,10 @@ constexpr int TL_THREADS = 256;
 constexpr int TL_NCHUNK = 2048;   // needles per CTA
 constexpr int TL_SUB = 1024;      // needles between candidate-queue drains
 constexpr int TL_QCAP = 2048;     // candidate queue entries
-constexpr int TL_DEFAULT_VARIANT = 3;  // 4 rows/thread, 6 CTAs/SM: fastest measured for q = 8 .. 256 (profiles/r01_scan_variants.log)
 
 template <int TL_ROWS, int MINB>   // rows per thread held in registers, min resident CTAs per SM
 __global__ void __launch_bounds__(TL_THREADS, MINB)
-match_tiled_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint4 *__restrict__ needles,
+match_tiled_kernel(DbPlanes rows, uint64_t n_rows, const uint4 *__restrict__ needles,
                    uint32_t q, uint32_t thr, Sink sink)
 {
     // dynamic shared memory sized by the launcher to the needle chunk actually present, so that small
@@ -195,7 +191,7 @@ match_tiled_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint4 
 #pragma unroll
     for (int u = 0; u < TL_ROWS; u++) {
         uint64_t r = tile + (uint64_t)u * TL_THREADS + threadIdx.x;
-        uint4 v = __ldg(rows + 2 * (r < n_rows ? r : 0));
+        uint4 v = __ldg(rows.pre + (r < n_rows ? r : 0));
         r012[u] = opaque(v.x ^ v.y ^ v.z);
         r0[u] = v.x;
         r1[u] = v.y;
@@ -225,7 +221,7 @@ match_tiled_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint4 
                         } else {  // queue full (adversarial data): verify in place
                             uint64_t r = tile + lrow;
                             if (r < n_rows) {
-                                const uint4 a0 = __ldg(rows + 2 * r), a1 = __ldg(rows + 2 * r + 1);
+                                const uint4 a0 = __ldg(rows.pre + r), a1 = __ldg(rows.suf + r);
                                 const uint4 *np2 = needles + (size_t)(n_first + i) * 2;
                                 uint32_t d = dist256(a0, a1, __ldg(np2), __ldg(np2 + 1));
                                 if (d <= thr)
@@ -248,7 +244,7 @@ match_tiled_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint4 
                 r = tile + (code >> 11);
                 nidx = n_first + (code & 2047u);
                 if (r < n_rows) {
-                    const uint4 a0 = __ldg(rows + 2 * r), a1 = __ldg(rows + 2 * r + 1);
+                    const uint4 a0 = __ldg(rows.pre + r), a1 = __ldg(rows.suf + r);
                     const uint4 *np2 = needles + (size_t)nidx * 2;
                     d = dist256(a0, a1, __ldg(np2), __ldg(np2 + 1));
                     hit = d <= thr;
@@ -263,166 +259,19 @@ match_tiled_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint4 
     }
 }
 
-// ----------------------------------------------------------- ALGO_STREAM --
-constexpr int ST_STAGES = 8;
-constexpr int ST_ROWS = 512;                   // rows per stage = consumer threads
-constexpr int ST_STAGE_BYTES = ST_ROWS * 32;   // 16 KB
-constexpr int ST_CONSUMER_WARPS = ST_ROWS / 32;
-constexpr int ST_THREADS = ST_ROWS + 32;       // + one producer warp
-constexpr int ST_MAXQ = 32;
-constexpr size_t ST_SMEM = (size_t)ST_STAGES * ST_STAGE_BYTES + 2 * ST_STAGES * sizeof(uint64_t);
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes,
-                                             uint64_t *bar)
-{
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-            "r"(smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
-        : "memory");
-}
-
-template <int NQ>  // needles rounded up to a multiple of 8 (8, 16, 24, 32)
-__global__ void __launch_bounds__(ST_THREADS, 1)
-match_stream_kernel(const uint8_t *__restrict__ rows, uint64_t n_rows,
-                    const uint4 *__restrict__ needles, uint32_t q, uint32_t thr, Sink sink)
-{
-    // needle prefixes: registers for up to 16 needles, shared memory (broadcast LDS) beyond
-    constexpr bool kRegs = NQ <= 16;
-    __shared__ uint4 spre[kRegs ? 1 : NQ];
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + (size_t)ST_STAGES * ST_STAGE_BYTES);
-    uint64_t *empty_bar = full_bar + ST_STAGES;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < ST_STAGES; s++) {
-            mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], ST_CONSUMER_WARPS);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    const uint64_t n_chunks = (n_rows + ST_ROWS - 1) / ST_ROWS;
-
-    if (warp == ST_CONSUMER_WARPS) {
-        // ===== producer: one lane streams the database with TMA bulk copies =====
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x, it++) {
-                const uint32_t s = it % ST_STAGES, use = it / ST_STAGES;
-                mbar_wait(&empty_bar[s], (use & 1u) ^ 1u);
-                const uint64_t first = c * ST_ROWS;
-                const uint32_t nr = (uint32_t)min((uint64_t)ST_ROWS, n_rows - first);
-                mbar_arrive_expect_tx(&full_bar[s], nr * 32u);
-                tma_bulk_g2s(smem + (size_t)s * ST_STAGE_BYTES, rows + first * 32u, nr * 32u,
-                             &full_bar[s]);
-            }
-        }
-        return;
-    }
-
-    // ===== consumers: one row per lane per stage =====
-    uint32_t n012[kRegs ? NQ : 1], n0[kRegs ? NQ : 1], n1[kRegs ? NQ : 1];
-    if constexpr (kRegs) {
-#pragma unroll
-        for (int j = 0; j < NQ; j++) {
-            // padding slots repeat the last needle: their bound never undercuts a real one
-            const uint4 n = __ldg(needles + 2 * min((uint32_t)j, q - 1));
-            n012[j] = opaque(n.x ^ n.y ^ n.z);
-            n0[j] = n.x;
-            n1[j] = n.y;
-        }
-    } else {
-        if (threadIdx.x < NQ) {
-            const uint4 n = __ldg(needles + 2 * min((uint32_t)threadIdx.x, q - 1));
-            spre[threadIdx.x] = make_uint4(n.x ^ n.y ^ n.z, n.x, n.y, n.w);
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(ST_ROWS) : "memory");  // consumer warps only
-    }
-    uint32_t it = 0;
-    for (uint64_t c = blockIdx.x; c < n_chunks; c += gridDim.x, it++) {
-        const uint32_t s = it % ST_STAGES, use = it / ST_STAGES;
-        mbar_wait(&full_bar[s], use & 1u);
-        const uint64_t r = c * ST_ROWS + threadIdx.x;
-        const uint4 *srow = reinterpret_cast<const uint4 *>(smem + (size_t)s * ST_STAGE_BYTES) +
-                            2 * threadIdx.x;
-        if (r < n_rows) {
-            const uint4 lo = srow[0];
-            const uint32_t r012 = opaque(lo.x ^ lo.y ^ lo.z);
-            uint32_t m = 0xffffffffu;
-#pragma unroll
-            for (int j = 0; j < NQ; j++) {
-                uint32_t lb;
-                if constexpr (kRegs) {
-                    lb = prefix96_lower_bound(r012, lo.x, lo.y, n012[j], n0[j], n1[j]);
-                } else {
-                    const uint4 pj = spre[j];
-                    lb = prefix96_lower_bound(r012, lo.x, lo.y, pj.x, pj.y, pj.z);
-                }
-                m = min(m, lb);
-            }
-            if (m <= thr) {  // rare: verify every needle on the full row (still in shared memory)
-                const uint4 hi = srow[1];
-                for (uint32_t j = 0; j < q; j++) {
-                    uint32_t d = dist256(lo, hi, __ldg(needles + 2 * j), __ldg(needles + 2 * j + 1));
-                    if (d <= thr)
-                        emit_single(sink, r, j, d);
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0)
-            mbar_arrive(&empty_bar[s]);
-    }
-}
-
 }  // namespace
 
 // --------------------------------------------------------------- launcher --
-int launch_match(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
+int launch_match(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
                  size_t q, uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
                  unsigned long long *min_key, int mode, int algo, int sm_count, cudaStream_t s,
-                 uint32_t needle_base)
+                 uint32_t needle_base, MatchStats *stats)
 {
     if (n_rows == 0 || q == 0)
         return 0;
     if (q > 0xffffffffull)
         return YUME_PDQ_CUDA_E_INVALID;
     Sink sink{out, cap, count, min_key, row_offset, (uint64_t)q, mode, needle_base};
-    const uint4 *rows4 = reinterpret_cast<const uint4 *>(rows);
     const uint4 *needles4 = reinterpret_cast<const uint4 *>(needles);
     if (algo == YUME_PDQ_CUDA_ALGO_AUTO) {
         // Measured on B200 (10M rows, threshold 31; profiles/r02*/quick.log): tiled POPC kernel 54 us for 8 needles, 86 us
@@ -437,13 +286,31 @@ int launch_match(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const 
             algo = YUME_PDQ_CUDA_ALGO_EXACT;
         else
             algo = YUME_PDQ_CUDA_ALGO_TILED;
+        // Data-dependent part (threshold <= 36, >= 512 needles): the paired prefix filter is only the faster tensor
+        // kernel while candidates are rare.  The previous launch on this haystack left its candidate rate in `stats`;
+        // past the break-even the next launches run the unfiltered 256-bit kernel, and the filter is probed again
+        // after 8, 16, ... 256 launches (back to 8 as soon as a probe finds the haystack sparse).
+        if (algo == YUME_PDQ_CUDA_ALGO_TENSOR && threshold <= 36 && q >= 512 && stats) {
+            const unsigned long long pairs_seen = stats->pairs, cand_seen = stats->candidates;
+            const bool dense = pairs_seen > 0 && (double)cand_seen > kPrefixFilterBreakEven * (double)pairs_seen;
+            if (stats->fallback_left > 0) {
+                stats->fallback_left--;
+                algo = YUME_PDQ_CUDA_ALGO_TENSOR_FULL;
+            } else if (dense) {
+                stats->fallback_interval = std::min<uint32_t>(std::max<uint32_t>(stats->fallback_interval * 2, 8), 256);
+                stats->fallback_left = stats->fallback_interval - 1;
+                stats->pairs = 0;          // the next probe's result decides again
+                stats->candidates = 0;
+                algo = YUME_PDQ_CUDA_ALGO_TENSOR_FULL;
+            } else {
+                stats->fallback_interval = 0;
+            }
+        }
     }
-    if (algo == YUME_PDQ_CUDA_ALGO_STREAM && q > ST_MAXQ)
-        algo = YUME_PDQ_CUDA_ALGO_TILED;
     // candidates of the 128-bit prefix filter: 4.6e-9 of the random pairs at threshold 31, 6e-7 at 36, 1.7e-5 at 40
     if (algo == YUME_PDQ_CUDA_ALGO_TENSOR_PAIRED || (algo == YUME_PDQ_CUDA_ALGO_TENSOR && threshold <= 36))
         return launch_match_tensor4x2(rows, n_rows, row_offset, needles, q, threshold, out, cap, count, min_key,
-                                      mode, sm_count, s, needle_base);
+                                      mode, sm_count, s, needle_base, stats);
     if (algo == YUME_PDQ_CUDA_ALGO_TENSOR && threshold <= 127)
         return launch_match_tensor4(rows, n_rows, row_offset, needles, q, threshold, out, cap, count, min_key,
                                     mode, sm_count, s, needle_base, -1);
@@ -457,60 +324,22 @@ int launch_match(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const 
     if (algo == YUME_PDQ_CUDA_ALGO_EXACT) {
         dim3 grid((unsigned)((n_rows + EX_THREADS * EX_ROWS - 1) / (EX_THREADS * EX_ROWS)),
                   (unsigned)((q + EX_NCHUNK - 1) / EX_NCHUNK));
-        match_exact_kernel<<<grid, EX_THREADS, 0, s>>>(rows4, n_rows, needles4, (uint32_t)q,
+        match_exact_kernel<<<grid, EX_THREADS, 0, s>>>(rows, n_rows, needles4, (uint32_t)q,
                                                        threshold, sink);
         YPDQ_LAUNCH_CHECK();
         return 0;
     }
     if (algo == YUME_PDQ_CUDA_ALGO_TILED) {
-        // 4 rows per thread and >= 6 resident CTAs per SM overlap one CTA's HBM loads with the others'
-        // popcounts (10M rows x 8 needles: 55 us vs 74 us with 8 rows / 116 registers)
-        static const int variant = [] {
-            const char *e = getenv("YPDQ_TILED_VARIANT");   // developer knob for tools/quick_bench.py
-            return e ? atoi(e) : -1;
-        }();
-        const int v = variant >= 0 ? variant : TL_DEFAULT_VARIANT;
-#define LAUNCH_TILED(R, B)                                                                         \
-    do {                                                                                          \
-        dim3 grid((unsigned)((n_rows + TL_THREADS * R - 1) / (TL_THREADS * R)),                   \
-                  (unsigned)((q + TL_NCHUNK - 1) / TL_NCHUNK));                                   \
-        const size_t smem = std::min<size_t>(q, TL_NCHUNK) * sizeof(uint4) + TL_QCAP * sizeof(uint32_t); \
-        match_tiled_kernel<R, B><<<grid, TL_THREADS, smem, s>>>(rows4, n_rows, needles4, (uint32_t)q, \
-                                                             threshold, sink);                    \
-    } while (0)
-        switch (v) {
-        case 1: LAUNCH_TILED(8, 4); break;
-        case 2: LAUNCH_TILED(4, 4); break;
-        case 3: LAUNCH_TILED(4, 6); break;
-        case 4: LAUNCH_TILED(4, 8); break;
-        case 5: LAUNCH_TILED(2, 8); break;
-        case 6: LAUNCH_TILED(16, 2); break;
-        case 7: LAUNCH_TILED(8, 3); break;
-        default: LAUNCH_TILED(8, 1); break;
-        }
-#undef LAUNCH_TILED
-        YPDQ_LAUNCH_CHECK();
-        return 0;
-    }
-    if (algo == YUME_PDQ_CUDA_ALGO_STREAM) {
-        const uint64_t n_chunks = (n_rows + ST_ROWS - 1) / ST_ROWS;
-        unsigned grid = (unsigned)std::min<uint64_t>(n_chunks, (uint64_t)sm_count);
-        const int nq8 = (int)((q + 7) / 8);
-#define LAUNCH_STREAM(NQ)                                                                         \
-    do {                                                                                          \
-        YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_stream_kernel<NQ>,                               \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,           \
-                                           (int)ST_SMEM));                                        \
-        match_stream_kernel<NQ><<<grid, ST_THREADS, ST_SMEM, s>>>(rows, n_rows, needles4,         \
-                                                                  (uint32_t)q, threshold, sink);  \
-    } while (0)
-        switch (nq8) {
-        case 1: LAUNCH_STREAM(8); break;
-        case 2: LAUNCH_STREAM(16); break;
-        case 3: LAUNCH_STREAM(24); break;
-        default: LAUNCH_STREAM(32); break;
-        }
-#undef LAUNCH_STREAM
+        // 4 rows per thread and >= 6 resident CTAs per SM overlap one CTA's HBM loads with the others' popcounts
+        // (profiles/r01_scan_variants.log: 8 rows x 3 CTAs, 2 x 8 and 16 x 2 are all slower)
+#ifndef TL_ROWS_CFG
+#define TL_ROWS_CFG 4
+#define TL_MINB_CFG 6
+#endif
+        constexpr int R = TL_ROWS_CFG, MINB = TL_MINB_CFG;
+        dim3 grid((unsigned)((n_rows + TL_THREADS * R - 1) / (TL_THREADS * R)), (unsigned)((q + TL_NCHUNK - 1) / TL_NCHUNK));
+        const size_t smem = std::min<size_t>(q, TL_NCHUNK) * sizeof(uint4) + TL_QCAP * sizeof(uint32_t);
+        match_tiled_kernel<R, MINB><<<grid, TL_THREADS, smem, s>>>(rows, n_rows, needles4, (uint32_t)q, threshold, sink);
         YPDQ_LAUNCH_CHECK();
         return 0;
     }

@@ -158,7 +158,7 @@ __device__ __forceinline__ void tc_emit(const TcSink &k, uint64_t local_row, uin
         : "r"(taddr))
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-match_tensor_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint8_t *__restrict__ needles_exp,
+match_tensor_kernel(DbPlanes rows, uint64_t n_rows, const uint8_t *__restrict__ needles_exp,
                     uint32_t n_mtiles, uint32_t q, int32_t dot_min, TcSink sink)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -290,8 +290,8 @@ match_tensor_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint8
                 const uint64_t row = nt * TC_N + r;
                 uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
                 if (row < n_rows) {
-                    lo = __ldg(rows + 2 * row);
-                    hi = __ldg(rows + 2 * row + 1);
+                    lo = __ldg(rows.pre + row);
+                    hi = __ldg(rows.suf + row);
                 }
                 const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
@@ -313,7 +313,7 @@ match_tensor_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint8
 
 }  // namespace
 
-int launch_match_tensor(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles, size_t q,
+int launch_match_tensor(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles, size_t q,
                         uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
                         unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base)
 {
@@ -336,7 +336,7 @@ int launch_match_tensor(const uint8_t *rows, size_t n_rows, uint64_t row_offset,
     const uint64_t n_ntiles = (n_rows + TC_N - 1) / TC_N;
     const unsigned grid = (unsigned)std::min<uint64_t>(n_ntiles, (uint64_t)sm_count);
     const int32_t dot_min = 256 - 2 * (int32_t)std::min<uint32_t>(threshold, 256u);
-    match_tensor_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(reinterpret_cast<const uint4 *>(rows), n_rows, exp, n_mtiles,
+    match_tensor_kernel<<<grid, TC_THREADS, TC_SMEM, s>>>(rows, n_rows, exp, n_mtiles,
                                                           (uint32_t)q, dot_min, sink);
     YPDQ_LAUNCH_CHECK();
     YPDQ_CUDA_TRY(cudaFreeAsync(exp, s));

@@ -190,7 +190,7 @@ __device__ __forceinline__ bool batch_any(const int32_t (&v)[T4_EB], int32_t min
 // columns; the loop over its set bits is not unrolled, so the rare path stays small.
 template <int KC>
 __device__ __forceinline__ void report_hits(const int32_t (&v)[T4_EB], int32_t min_bits, uint64_t row0, uint64_t n_rows,
-                                            uint32_t needle, const uint4 *__restrict__ rows, const Tc4Sink &sink)
+                                            uint32_t needle, const DbPlanes &rows, const Tc4Sink &sink)
 {
     if (KC == 8) {
 #pragma unroll
@@ -220,7 +220,7 @@ __device__ __forceinline__ void report_hits(const int32_t (&v)[T4_EB], int32_t m
             mw &= mw - 1;
             if (row >= n_rows)
                 continue;
-            const uint4 a0 = __ldg(rows + 2 * row), a1 = __ldg(rows + 2 * row + 1);
+            const uint4 a0 = __ldg(rows.pre + row), a1 = __ldg(rows.suf + row);
             const uint32_t dist = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) +
                                   __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) +
                                   __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
@@ -232,7 +232,7 @@ __device__ __forceinline__ void report_hits(const int32_t (&v)[T4_EB], int32_t m
 
 template <int KC>
 __global__ void __launch_bounds__(T4_THREADS, 1)
-match_tensor4_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint8_t *__restrict__ needles_exp,
+match_tensor4_kernel(DbPlanes rows, uint64_t n_rows, const uint8_t *__restrict__ needles_exp,
                      uint32_t n_mtiles, uint32_t q, int32_t min_bits, Tc4Sink sink)
 {
     using Cfg = T4Cfg<KC>;
@@ -352,9 +352,9 @@ match_tensor4_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint
                     lo[h] = make_uint4(0, 0, 0, 0);
                     hi[h] = lo[h];
                     if (r < T4_ROWS && row < n_rows) {
-                        lo[h] = __ldg(rows + 2 * row);
+                        lo[h] = __ldg(rows.pre + row);
                         if (KC == 8)
-                            hi[h] = __ldg(rows + 2 * row + 1);
+                            hi[h] = __ldg(rows.suf + row);
                     }
                 }
                 if (g == 0)
@@ -426,7 +426,7 @@ match_tensor4_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint
 }
 
 template <int KC>
-static int launch_tc4(const uint8_t *rows, size_t n_rows, const uint8_t *needles, size_t q, uint32_t threshold,
+static int launch_tc4(DbPlanes rows, size_t n_rows, const uint8_t *needles, size_t q, uint32_t threshold,
                       const Tc4Sink &sink, int sm_count, cudaStream_t s)
 {
     using Cfg = T4Cfg<KC>;
@@ -451,7 +451,7 @@ static int launch_tc4(const uint8_t *rows, size_t n_rows, const uint8_t *needles
     // per launch: function attributes are per device, and the call costs microseconds
     YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor4_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)t4_smem<KC>()));
-    match_tensor4_kernel<KC><<<grid, T4_THREADS, t4_smem<KC>(), s>>>(reinterpret_cast<const uint4 *>(rows), n_rows, exp,
+    match_tensor4_kernel<KC><<<grid, T4_THREADS, t4_smem<KC>(), s>>>(rows, n_rows, exp,
                                                                      n_mtiles, (uint32_t)q, min_bits, sink);
     YPDQ_LAUNCH_CHECK();
     YPDQ_CUDA_TRY(cudaFreeAsync(exp, s));
@@ -462,7 +462,7 @@ static int launch_tc4(const uint8_t *rows, size_t n_rows, const uint8_t *needles
 
 // prefix = -1: automatic (prefix filter when the threshold makes candidates rare), 0: full 256-bit dot products,
 // 1: 128-bit prefix filter
-int launch_match_tensor4(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles, size_t q,
+int launch_match_tensor4(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles, size_t q,
                          uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
                          unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base,
                          int prefix)

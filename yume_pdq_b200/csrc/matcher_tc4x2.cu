@@ -84,7 +84,7 @@ constexpr uint32_t X2_LBO = 128;               // bytes between K-adjacent 16-by
 // constants, used by the high field; every MMA reads two adjacent blocks
 constexpr uint32_t X2_A_SBO = 6 * 128;
 constexpr int X2_A_BYTES = (X2_M / 8) * X2_A_SBO;     // 12 KB
-constexpr int X2_RAW_BYTES = X2_ROWS * 32;             // 30 KB: the packed rows of a unit as they lie in HBM
+constexpr int X2_RAW_BYTES = X2_ROWS * 16;             // 15 KB: the 16-byte prefixes of a unit's rows as they lie in HBM
 // Warp roles.  Three configurations of the same kernel:
 //  * X2Large (12 epilogue warps x 80 columns, 2 row warps; 16 warps x 128 registers): many needle tiles per unit,
 //    the epilogue is the bottleneck (8 / 12 / 16 epilogue warps: 29.2 / 29.9 / 28.2e12 pairs/s);
@@ -94,7 +94,7 @@ constexpr int X2_RAW_BYTES = X2_ROWS * 32;             // 30 KB: the packed rows
 //  * X2One: X2Small's roles for a single needle tile (see ONE_TILE).
 // Warps [0, EPI) are epilogue warps (whole warpgroups); of the following warps two are the producer and the MMA
 // issuer, the others mask rows.
-// The packed rows reach shared memory by TMA bulk copies (producer lane -> RAW ring, 30 KB per unit) and are masked
+// The packed rows reach shared memory by TMA bulk copies (producer lane -> RAW ring, 15 KB per unit) and are masked
 // from there.  They must not be prefetched into registers: fence.proxy.async (needed between the masked st.shared
 // and the MMAs) is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC in SASS, and the membar waits for every global load the thread
 // has in flight -- with register prefetching a <= 128-needle scan took MMA time PLUS HBM time (106 us for 10M rows;
@@ -105,7 +105,7 @@ constexpr int X2_RAW_BYTES = X2_ROWS * 32;             // 30 KB: the packed rows
 template <int EPI, int EXP, int ASTAGES, int RAWSTAGES, bool ONE = false>
 struct X2Cfg {
     static constexpr int A_STAGES = ASTAGES;        // needle-tile ring slots (12 KB)
-    static constexpr int RAW_STAGES = RAWSTAGES;    // packed-row ring slots (30 KB)
+    static constexpr int RAW_STAGES = RAWSTAGES;    // row-prefix ring slots (15 KB)
     static constexpr int B_BUFS = 2;                // masked row buffers (60 KB): unit i lives in buffer i % B_BUFS
     static constexpr size_t SMEM = B_BUFS * (size_t)X2_SB_BYTES + ASTAGES * (size_t)X2_A_BYTES + RAWSTAGES * (size_t)X2_RAW_BYTES + 512;   // + 33 mbarriers and the TMEM address
     static_assert(SMEM <= 232448, "shared memory per CTA");
@@ -122,9 +122,9 @@ struct X2Cfg {
     static constexpr int REGS_EPI = 176, REGS_OTHER = 80;
     static_assert(!SPLIT_REGS || 32 * (EPI * REGS_EPI + (EXP + 2) * REGS_OTHER) <= 65536 / THREADS / 8 * 8 * THREADS, "register pool");
 };
-using X2Large = X2Cfg<12, 2, 4, 1>;          // 120 + 48 + 30 KB
-using X2Small = X2Cfg<8, 6, 2, 2>;           // 120 + 24 + 60 KB
-using X2One = X2Cfg<8, 6, 1, 3, true>;       // 120 + 12 + 90 KB
+using X2Large = X2Cfg<12, 2, 4, 2>;          // 120 + 48 + 30 KB
+using X2Small = X2Cfg<8, 6, 4, 3>;           // 120 + 48 + 45 KB
+using X2One = X2Cfg<8, 6, 1, 4, true>;       // 120 + 12 + 60 KB
 // needle tiles (of 128) up to which X2Small is used; measured on 10M rows: 768 needles 0.36 ms (Small) vs 0.42 (Large),
 // 1024: 0.44 vs 0.42, 1536: 0.61 vs 0.57, 2048: 0.80 vs 0.73
 constexpr uint32_t X2_SMALL_MAX_TILES = 7;
@@ -132,8 +132,8 @@ constexpr uint32_t X2_SF_B = 480, X2_SF_LO = 488, X2_SF_HI = 496;   // TMEM colu
 constexpr uint32_t X2_BITS_BASE = 0x4B400000u;       // bit pattern of 1.5 * 2^23
 constexpr int X2_BIAS_ELEMS = 6;                     // element positions of the high field that hold constants
 constexpr uint32_t X2_ROW_BIAS = 0x00777777u, X2_NEEDLE_BIAS = 0x00477777u;   // e2m1 6.0 = 0x7, 2.0 = 0x4
-// Units the producer lane prefetches into L2 ahead of the TMA row copies (cp.async.bulk.prefetch.L2, 30 KB each): the
-// RAW ring alone keeps only 30..90 KB per SM in flight, which does not cover the HBM latency under load.
+// Units the producer lane prefetches into L2 ahead of the TMA row copies (cp.async.bulk.prefetch.L2, 15 KB each): the
+// RAW ring alone keeps only 30..60 KB per SM in flight, which does not cover the HBM latency under load.
 #ifndef X2_PREFETCH_UNITS_CFG
 #define X2_PREFETCH_UNITS_CFG 6
 #endif
@@ -237,16 +237,19 @@ struct X2Candidate {
     uint32_t needle;
     uint32_t pad;
 };
-constexpr uint32_t X2_CAND_SLOTS = 1024;   // per epilogue warp
+#ifndef X2_CAND_SLOTS_CFG
+#define X2_CAND_SLOTS_CFG 1024
+#endif
+constexpr uint32_t X2_CAND_SLOTS = X2_CAND_SLOTS_CFG;   // per epilogue warp
 struct X2CandList {
     X2Candidate *items;     // [gridDim.x * X2_EPI_WARPS][X2_CAND_SLOTS]
     uint32_t *counts;       // [gridDim.x * X2_EPI_WARPS]
 };
 
-__device__ __forceinline__ void x2_verify(uint64_t row, uint32_t needle, const uint4 *__restrict__ rows, const Tc4Sink &sink)
+__device__ __forceinline__ void x2_verify(uint64_t row, uint32_t needle, const DbPlanes &rows, const Tc4Sink &sink)
 {
     const uint4 b0 = __ldg(sink.needles_raw + 2 * (size_t)needle), b1 = __ldg(sink.needles_raw + 2 * (size_t)needle + 1);
-    const uint4 a0 = __ldg(rows + 2 * row), a1 = __ldg(rows + 2 * row + 1);
+    const uint4 a0 = __ldg(rows.pre + row), a1 = __ldg(rows.suf + row);
     const uint32_t dist = hamming256(a0, a1, b0, b1);
     if (dist <= sink.threshold)
         tc4_emit(sink, row, needle, dist);
@@ -255,7 +258,7 @@ __device__ __forceinline__ void x2_verify(uint64_t row, uint32_t needle, const u
 // rare path, entered by the whole warp: both rows of every flagged column of every lane become candidates
 template <int W>
 __device__ __forceinline__ void x2_report(const int32_t (&v)[W], int32_t lo_min, int32_t hi_min, uint64_t row0, uint64_t n_rows,
-                                          uint32_t needle, bool needle_ok, uint32_t lane, const uint4 *__restrict__ rows,
+                                          uint32_t needle, bool needle_ok, uint32_t lane, const DbPlanes &rows,
                                           const Tc4Sink &sink, X2Candidate *region, uint32_t &n_cand)
 {
     static_assert(W % 8 == 0, "groups of 8 columns");
@@ -297,10 +300,19 @@ __device__ __forceinline__ void x2_report(const int32_t (&v)[W], int32_t lo_min,
     }
 }
 
-// one CTA per candidate region (= epilogue warp of the scan)
+// one CTA per candidate region (= epilogue warp of the scan); also leaves the launch's candidate total for the host
 __global__ void __launch_bounds__(128)
-verify_candidates_kernel(const uint4 *__restrict__ rows, X2CandList cand, Tc4Sink sink)
+verify_candidates_kernel(DbPlanes rows, X2CandList cand, Tc4Sink sink, MatchStats *stats, unsigned long long pairs,
+                         unsigned long long *tally /* device: {sum of counts, CTAs done}, zeroed */)
 {
+    if (stats && threadIdx.x == 0) {
+        atomicAdd(&tally[0], (unsigned long long)cand.counts[blockIdx.x]);
+        __threadfence();
+        if (atomicAdd(&tally[1], 1ull) == gridDim.x - 1) {     // last CTA: plain stores into the mapped host struct
+            stats->candidates = atomicAdd(&tally[0], 0ull);
+            stats->pairs = pairs;
+        }
+    }
     const uint32_t n = min(cand.counts[blockIdx.x], X2_CAND_SLOTS);
     const X2Candidate *region = cand.items + (size_t)blockIdx.x * X2_CAND_SLOTS;
     for (uint32_t i = threadIdx.x; i < n; i += 128)
@@ -338,7 +350,7 @@ struct X2Cursor {
 template <class Cfg>
 __device__ __forceinline__ void x2_epilogue(uint32_t tmem, uint32_t quad, uint32_t part, uint32_t lane, uint64_t *d_full,
                                             uint64_t *d_empty, const X2Units &units, uint32_t q, const int2 *__restrict__ mins,
-                                            uint64_t n_rows, const uint4 *__restrict__ rows, const Tc4Sink &sink,
+                                            uint64_t n_rows, const DbPlanes &rows, const Tc4Sink &sink,
                                             const X2CandList &cand)
 {
     constexpr int X2_EB = Cfg::EB;
@@ -427,7 +439,7 @@ __device__ __forceinline__ void x2_epilogue(uint32_t tmem, uint32_t quad, uint32
 
 template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
-match_tensor4x2_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const uint8_t *__restrict__ needles_exp,
+match_tensor4x2_kernel(DbPlanes rows, uint64_t n_rows, const uint8_t *__restrict__ needles_exp,
                        X2Units units, uint32_t q, const int2 *__restrict__ mins, Tc4Sink sink, X2CandList cand)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -435,7 +447,7 @@ match_tensor4x2_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const ui
     uint8_t *sB = smem;                                      // B_BUFS x 60 KB masked row tiles
     constexpr uint32_t NB = Cfg::B_BUFS;
     uint8_t *sA = smem + NB * X2_SB_BYTES;                   // A_STAGES x 12 KB needle tiles
-    uint8_t *sR = sA + X2_A_STAGES * X2_A_BYTES;             // RAW_STAGES x 30 KB packed rows
+    uint8_t *sR = sA + X2_A_STAGES * X2_A_BYTES;             // RAW_STAGES x 15 KB row prefixes
     uint64_t *bars = reinterpret_cast<uint64_t *>(sR + X2_RAW_STAGES * X2_RAW_BYTES);
     uint64_t *a_full = bars, *a_empty = bars + 4, *b_full = bars + 8, *b_empty = bars + 12;
     uint64_t *d_full = bars + 16, *d_empty = bars + 20, *r_full = bars + 24, *r_empty = bars + 28;
@@ -496,9 +508,9 @@ match_tensor4x2_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const ui
         // ===== needle tile producer =====
         if constexpr (Cfg::SPLIT_REGS)
             asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_OTHER));
-        auto unit_bytes = [&](uint64_t st) { return (uint32_t)min((uint64_t)X2_ROWS, n_rows - st * X2_ROWS) * 32u; };
+        auto unit_bytes = [&](uint64_t st) { return (uint32_t)min((uint64_t)X2_ROWS, n_rows - st * X2_ROWS) * 16u; };
         auto prefetch_unit = [&](uint64_t st) {
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rows + 2 * st * X2_ROWS), "r"(unit_bytes(st)) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rows.pre + st * X2_ROWS), "r"(unit_bytes(st)) : "memory");
         };
         if (lane == 0) {
             // (1) L2 prefetch of the unit X2_PREFETCH_UNITS ahead, (2) TMA copy of the packed rows of the unit
@@ -512,7 +524,7 @@ match_tensor4x2_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const ui
                 bar_wait(&r_empty[sl], (use & 1u) ^ 1u);
                 const uint32_t bytes = unit_bytes(raw.st);
                 bar_expect_tx(&r_full[sl], bytes);
-                bulk_g2s(sR + (size_t)sl * X2_RAW_BYTES, rows + 2 * raw.st * X2_ROWS, bytes, &r_full[sl]);
+                bulk_g2s(sR + (size_t)sl * X2_RAW_BYTES, rows.pre + raw.st * X2_ROWS, bytes, &r_full[sl]);
                 raw.next(units);
                 ir++;
             };
@@ -610,7 +622,7 @@ match_tensor4x2_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const ui
                 const uint32_t r = t + X2_EXP_THREADS * h;
                 rw[h] = make_uint4(0, 0, 0, 0);
                 if (r < left)
-                    rw[h] = src[2 * r];
+                    rw[h] = src[r];
             }
             bar_wait(&b_empty[b], ((i / NB) & 1u) ^ 1u);
             if (t == 0) X2_TR(0, i);
@@ -652,9 +664,10 @@ match_tensor4x2_kernel(const uint4 *__restrict__ rows, uint64_t n_rows, const ui
 }  // namespace
 
 // 128 / 122-bit prefix filter, two rows per accumulator column (threshold <= 60; candidates verified with POPC)
-int launch_match_tensor4x2(const uint8_t *rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles, size_t q,
+int launch_match_tensor4x2(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles, size_t q,
                            uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
-                           unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base)
+                           unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base,
+                           MatchStats *stats)
 {
     if (n_rows == 0 || q == 0)
         return 0;
@@ -681,19 +694,19 @@ int launch_match_tensor4x2(const uint8_t *rows, size_t n_rows, uint64_t row_offs
     const bool small = n_mtiles <= X2_SMALL_MAX_TILES;
     const size_t n_regions = (size_t)grid * (small ? X2Small::EPI_WARPS : X2Large::EPI_WARPS), count_bytes = (n_regions * 4 + 255) / 256 * 256;
     uint8_t *exp = nullptr;
-    cudaError_t e = cudaMallocAsync(&exp, exp_bytes + count_bytes + n_regions * X2_CAND_SLOTS * sizeof(X2Candidate), s);
+    const size_t scratch_bytes = exp_bytes + count_bytes + n_regions * X2_CAND_SLOTS * sizeof(X2Candidate);
+    cudaError_t e = cudaMallocAsync(&exp, scratch_bytes + 16, s);
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         return e == cudaErrorMemoryAllocation ? YUME_PDQ_CUDA_E_NOMEM : (int)e;
     }
     X2CandList cand{reinterpret_cast<X2Candidate *>(exp + exp_bytes + count_bytes), reinterpret_cast<uint32_t *>(exp + exp_bytes)};
     int2 *mins = reinterpret_cast<int2 *>(exp + tile_bytes);
-    const uint4 *rows4 = reinterpret_cast<const uint4 *>(rows);
     if (one) {
         static_assert(X2One::THREADS == X2Small::THREADS && X2One::EPI_WARPS == X2Small::EPI_WARPS, "same launch shape");
         YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor4x2_kernel<X2One>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)X2One::SMEM));
-        match_tensor4x2_kernel<X2One><<<grid, X2One::THREADS, X2One::SMEM, s>>>(rows4, n_rows, nullptr, units, (uint32_t)q, nullptr,
+        match_tensor4x2_kernel<X2One><<<grid, X2One::THREADS, X2One::SMEM, s>>>(rows, n_rows, nullptr, units, (uint32_t)q, nullptr,
                                                                             sink, cand);
         YPDQ_LAUNCH_CHECK();
         YPDQ_CUDA_TRY(cudaFreeAsync(exp, s));
@@ -709,13 +722,16 @@ int launch_match_tensor4x2(const uint8_t *rows, size_t n_rows, uint64_t row_offs
     YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_tensor4x2_kernel<X2Small>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)X2Small::SMEM));
     if (small)
-        match_tensor4x2_kernel<X2Small><<<grid, X2Small::THREADS, X2Small::SMEM, s>>>(rows4, n_rows, exp, units, (uint32_t)q, mins,
+        match_tensor4x2_kernel<X2Small><<<grid, X2Small::THREADS, X2Small::SMEM, s>>>(rows, n_rows, exp, units, (uint32_t)q, mins,
                                                                                 sink, cand);
     else
-        match_tensor4x2_kernel<X2Large><<<grid, X2Large::THREADS, X2Large::SMEM, s>>>(rows4, n_rows, exp, units, (uint32_t)q, mins,
+        match_tensor4x2_kernel<X2Large><<<grid, X2Large::THREADS, X2Large::SMEM, s>>>(rows, n_rows, exp, units, (uint32_t)q, mins,
                                                                                 sink, cand);
     YPDQ_LAUNCH_CHECK();
-    verify_candidates_kernel<<<(unsigned)n_regions, 128, 0, s>>>(rows4, cand, sink);
+    unsigned long long *tally = reinterpret_cast<unsigned long long *>(exp + scratch_bytes);
+    if (stats)
+        YPDQ_CUDA_TRY(cudaMemsetAsync(tally, 0, 16, s));
+    verify_candidates_kernel<<<(unsigned)n_regions, 128, 0, s>>>(rows, cand, sink, stats, (unsigned long long)n_rows * q, tally);
     YPDQ_LAUNCH_CHECK();
     YPDQ_CUDA_TRY(cudaFreeAsync(exp, s));
     return 0;
