@@ -54,6 +54,12 @@ FRAMES_PER_GPU = 4096
 THRESHOLD = 31
 SEED = 0x79756D652D706471
 N_PLANT = 64
+# DRAM bytes (read + written) per database row / per frame that ONE launch of each kernel moved under `ncu --set full`
+# at the default sizes (tools/ncu_full.sh -> profiles/r02q/traffic.csv); None = not captured for this build
+TRAFFIC_SOURCE = "profiles/r02q/traffic.csv (ncu --set full of this build's kernels, one GPU, default sizes)"
+TRAFFIC_TENSOR_PER_ROW = None
+TRAFFIC_HASH_PER_FRAME = None
+TRAFFIC_SCAN_PER_ROW = None
 
 
 def env_int(name, default):
@@ -266,6 +272,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison on the sub-sampled problem")
     ap.add_argument("--no-config4", action="store_true")
+    ap.add_argument("--no-worst-case", action="store_true", help="skip the clustered-haystack leg")
     ap.add_argument("--no-config5", action="store_true")
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help=argparse.SUPPRESS)
     ap.add_argument("--db-rows", type=int, default=DB_ROWS, help=argparse.SUPPRESS)
@@ -442,12 +449,13 @@ def main():
         ts = [a.elapsed_time(b) for a, b in ev]
         return float(np.mean(ts)), float(np.median(ts)), float(np.min(ts))
 
-    # DRAM traffic per launch from the ncu captures under profiles/ (bytes read + written), per row / per frame;
-    # reported only for the sizes those captures were taken at (one GPU, the default DB, f32 frames)
+    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the ncu --set full captures of THIS
+    # round's kernels (profiles/r02q/traffic.csv, one GPU, default sizes), scaled per row / per frame; null elsewhere
     default_sizes = n_gpus == 1 and DB_ROWS == (10_000_000 // 2048 + 1) * 2048
-    traffic_tensor = (324819200 + 3689984) / 10_000_384 * shard_rows if default_sizes and B == 4096 else None
-    traffic_hash = (1235472640 + 4763904) / 1184 * B if default_sizes else None
-    traffic_scan = (320080128 + 5022464) / 10_000_384 * shard_rows if default_sizes else None
+    traffic_tensor = TRAFFIC_TENSOR_PER_ROW * shard_rows if default_sizes and B == 4096 and TRAFFIC_TENSOR_PER_ROW else None
+    traffic_hash = TRAFFIC_HASH_PER_FRAME * B if default_sizes and TRAFFIC_HASH_PER_FRAME else None
+    traffic_scan = TRAFFIC_SCAN_PER_ROW * shard_rows if default_sizes and TRAFFIC_SCAN_PER_ROW else None
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     line_extra = {}
     mxf4_peak, mxf4_clk = yp.measure_mxf4_peak(local_rank, 20000)
     flush = torch.zeros(64 << 20, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
@@ -463,9 +471,12 @@ def main():
     n8 = nd[:8].contiguous()
     s_mean, s_med, s_min = time_kernel(
         lambda: matcher.find_device(n8, 8, match_out, CAP, match_cnt), 20, flush)
+    rows_in_m = shard_rows >= 2_000_000          # ALGO_AUTO's rule for <= 16 needles at threshold <= 40 (matcher.cu)
+    p_mean, _, _ = time_kernel(
+        lambda: matcher.find_device(n8, 8, match_out, CAP, match_cnt, algo=yp.ALGO_TILED), 20, flush)
     # (3b) the needle counts of the reference's batched CpuMatcher<B, N> and of a 128-frame video chunk
     batch_us = {}
-    for qb in (32, 128, 1024):
+    for qb in (16, 32, 128, 1024):
         if qb <= q_loc:
             nb = nd[:qb].contiguous()
             b_mean, _, _ = time_kernel(lambda: matcher.find_device(nb, qb, match_out, CAP, match_cnt), 10, flush)
@@ -495,6 +506,9 @@ def main():
             sharded_scan()
             ts.append((time.perf_counter() - t0) * 1e6)
         sharded_e2e = max_over_ranks(float(np.median(ts)))
+    worst = None
+    if rank == 0 and not args.no_worst_case:
+        worst = worst_case_leg(args, yp, torch, dev, local_rank, shard_rows, flush)
     del flush
 
     if rank == 0:
@@ -527,23 +541,40 @@ def main():
             "tensor_ops_per_pair": ops_per_pair, "executed_tensor_ops_per_pair": ops_per_pair,
             "executed_frac": achieved_tops / mxf4_peak,
             "tpairs_per_s": pairs / (m_mean * 1e-3) / 1e12,
-            "traffic": traffic_tensor, "traffic_source": "profiles/r01ak/traffic_tensor32k.csv (ncu, same sizes)",
+            "traffic": traffic_tensor, "traffic_source": TRAFFIC_SOURCE,
             "ms_per_launch": m_mean, "share_of_step": share,
         }
         line_extra["roofline_hash"] = {
             "kernel": "hash_fused_kernel", "bound": "hbm", "achieved": hash_bytes / (h_mean * 1e-3) / 1e9,
             "peak": hbm_peak, "unit": "GB/s", "frac": hash_bytes / (h_mean * 1e-3) / 1e9 / hbm_peak,
             "peak_source": peak_src, "traffic": traffic_hash, "algorithmic_bytes": hash_bytes,
-            "traffic_source": "profiles/r01ak/traffic_hash.csv (ncu, scaled per frame)", "ms_per_launch": h_mean,
+            "traffic_source": TRAFFIC_SOURCE, "ms_per_launch": h_mean,
             "images_per_s": B / (h_mean * 1e-3),
         }
+        # The haystack lies in HBM as two 16-byte planes (prefix / suffix) and the scan's prefix filter streams the
+        # first one only: the bytes the kernel must move are 16 per row ("algorithmic_bytes"), the database it covers
+        # is 32 per row ("db_gbs", the metric BASELINE.json names).  With half the bytes to move the kernel is bound
+        # by the POPC (XU) pipe: 2 POPC per (row, needle) pair at 16 per clock and SM.
+        sm_clk = float(clocks.get("sm_mhz") or 1965.0) * 1e6
+        popc_peak = 16.0 * sm_count * sm_clk
         line_extra["scan"] = {
-            "kernel": "8 needles x %d rows, threshold %d" % (shard_rows, THRESHOLD),
+            "kernel": "%s: 8 needles x %d rows, threshold %d" % (
+                "match_rows_m_kernel (tcgen05.mma kind::mxf4, database rows in the M dimension, operand A written to tensor "
+                "memory from registers)" if rows_in_m else "match_tiled_kernel (POPC prefix filter)", shard_rows, THRESHOLD),
             "us": s_mean * 1e3, "us_median": s_med * 1e3, "us_min": s_min * 1e3,
-            "db_gbs": scan_bytes / (s_mean * 1e-3) / 1e9, "bound": "hbm", "peak": hbm_peak,
-            "frac": scan_bytes / (s_mean * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src,
-            "rows_per_s": shard_rows / (s_mean * 1e-3), "traffic": traffic_scan, "algorithmic_bytes": scan_bytes,
-            "traffic_source": "profiles/r01ak/traffic_scan.csv (ncu, same sizes)",
+            "db_gbs": scan_bytes / (s_mean * 1e-3) / 1e9,
+            "db_gbs_note": "database bytes covered per second (32 B per row); may exceed the HBM peak because only the prefix plane is read",
+            "algorithmic_bytes": shard_rows * 16, "hbm_gbs": shard_rows * 16 / (s_mean * 1e-3) / 1e9,
+            "bound": ("alu pipe (row -> e2m1 operand masking, 22 integer instructions per row) + launch latency" if rows_in_m else
+                      "xu (POPC pipe) + launch latency"), "peak": hbm_peak,
+            "frac": shard_rows * 16 / (s_mean * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src,
+            "popc_scan": {
+                "kernel": "match_tiled_kernel forced (ALGO_TILED): the XU-bound alternative, ALGO_AUTO's choice below 2M rows",
+                "us": p_mean * 1e3, "popc_per_pair": 2, "popc_rate": 2.0 * shard_rows * 8 / (p_mean * 1e-3),
+                "popc_peak": popc_peak, "popc_frac": 2.0 * shard_rows * 8 / (p_mean * 1e-3) / popc_peak,
+                "popc_peak_source": "16 POPC / clk / SM x %d SMs x %.0f MHz (median SM clock of this run)" % (sm_count, sm_clk / 1e6)},
+            "rows_per_s": shard_rows / (s_mean * 1e-3), "traffic": traffic_scan,
+            "traffic_source": TRAFFIC_SOURCE,
             "needle_batches_us": batch_us,
             "sharded_e2e_us": sharded_e2e,
             "sharded_e2e_path": None if n_gpus == 1 else
@@ -654,7 +685,7 @@ def main():
             "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks,
             "matches_per_step": total_matches, "planted": N_PLANT * n_gpus,
             "parity_checked": bool(parity and parity.get("checked")), "parity": parity,
-            "config5": c5, "config4": c4,
+            "config5": c5, "config4": c4, "worst_case": worst,
             "cpu_baseline": cpu_bl,
         }
         line.update(line_extra)
@@ -663,6 +694,124 @@ def main():
     if n_gpus > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def worst_case_leg(args, yp, torch, dev, local_rank, rows_n, flush):
+    """ALGO_AUTO on haystacks that are NOT random (one GPU, this rank's row count), threshold 31, 32768 needles:
+      * "families": 0.1 % of the rows lie within 0..40 bits of one of 32 base hashes and the needles are 32 'videos' of
+        1024 near-identical frames (within 6 bits of a base) -- every such row is a prefix-filter candidate against 1024
+        needles (3e-5 of all pairs), most of them real matches.  All needles of a tile flag the same accumulator column,
+        so few accumulator batches take the filter's rare path and the filter stays the fast kernel;
+      * "scattered": 10 % of the rows are each within 0..40 bits of ONE random needle -- a million separate flagged
+        batches, most of them matches, which the unfiltered kernel pays ~115 ns each for: the filter stays;
+      * "prefix_twins": 25 % of the rows share their first 128 bits (within 0..31 bits) with one random needle but not
+        the rest -- candidates that are not matches, 4 % of the accumulator batches flag: ALGO_AUTO falls back to the
+        unfiltered kernel.
+    For each: steady-state rate of ALGO_AUTO, of the prefix filter forced on, of the unfiltered kernel forced on.
+    `worst_case.tpairs_per_s` is the slowest of the ALGO_AUTO rates."""
+    rng = np.random.default_rng(4242)
+    q = 32768
+
+    def flipped(base_rows, k):
+        """each 32-byte row with exactly k[i] distinct random bits flipped"""
+        order = np.argsort(rng.random((base_rows.shape[0], 256)), axis=1)
+        mask = (order < k[:, None]).astype(np.uint8)
+        return np.packbits(np.unpackbits(base_rows, axis=1) ^ mask, axis=1)
+
+    def dist(a, b):
+        return np.bitwise_count(a ^ b).sum(axis=-1, dtype=np.int32)
+
+    def scenario(kind):
+        if kind == "families":
+            n_cl, per = 32, 1024
+            bases = rng.integers(0, 256, size=(n_cl, 32), dtype=np.uint8)
+            needles = flipped(np.repeat(bases, per, axis=0), rng.integers(0, 7, size=q))
+            n_near = max(n_cl, rows_n // 1000)
+            near_cl = rng.integers(0, n_cl, size=n_near)
+            near = flipped(bases[near_cl], rng.integers(0, 41, size=n_near))
+            expect = 0
+            for c in range(n_cl):
+                rc = near[near_cl == c]
+                if rc.shape[0]:
+                    expect += int((dist(rc[:, None, :], needles[None, c * per:(c + 1) * per, :]) <= THRESHOLD).sum())
+            what = "%d rows (0.1 %%) within 0..40 bits of one of %d bases; needles = %d x %d frames within 6 bits of a base" % (
+                n_near, n_cl, n_cl, per)
+            cand_frac = n_near * per / (rows_n * q)
+        elif kind == "scattered":
+            needles = rng.integers(0, 256, size=(q, 32), dtype=np.uint8)
+            n_near = rows_n // 10
+            of = rng.integers(0, q, size=n_near)
+            near = np.concatenate([flipped(needles[of[i:i + 65536]], rng.integers(0, 41, size=len(of[i:i + 65536])))
+                                   for i in range(0, n_near, 65536)])
+            expect = int((dist(near, needles[of]) <= THRESHOLD).sum())
+            what = "%d rows (10 %%) each within 0..40 bits of one random needle of %d" % (n_near, q)
+            cand_frac = n_near / (rows_n * q)
+        else:
+            needles = rng.integers(0, 256, size=(q, 32), dtype=np.uint8)
+            n_near = rows_n // 4
+            of = rng.integers(0, q, size=n_near)
+            near = rng.integers(0, 256, size=(n_near, 32), dtype=np.uint8)          # random suffix ...
+            for i in range(0, n_near, 65536):                                        # ... prefix of a needle, 0..31 bits flipped
+                blk = of[i:i + 65536]
+                pre = np.concatenate([needles[blk, :16], np.zeros((len(blk), 16), dtype=np.uint8)], axis=1)
+                order = np.argsort(rng.random((len(blk), 128)), axis=1)
+                mask = np.concatenate([(order < rng.integers(0, 32, size=len(blk))[:, None]).astype(np.uint8),
+                                       np.zeros((len(blk), 128), dtype=np.uint8)], axis=1)
+                near[i:i + len(blk), :16] = np.packbits(np.unpackbits(pre, axis=1) ^ mask, axis=1)[:, :16]
+            expect = int((dist(near, needles[of]) <= THRESHOLD).sum())
+            what = "%d rows (25 %%) whose first 128 bits are within 0..31 bits of one random needle of %d, the rest random" % (n_near, q)
+            cand_frac = n_near / (rows_n * q)
+        where = rng.choice(rows_n, size=n_near, replace=False)
+        rows_t = torch.empty((rows_n, 32), dtype=torch.uint8, device=dev)
+        yp.synth_rows(rows_t, rows_n, first_row=1 << 40, seed=SEED, device=local_rank)
+        rows_t[torch.from_numpy(where).to(dev)] = torch.from_numpy(near).to(dev)
+        dbc = yp.CudaVectorDatabase(rows_t, device=local_rank)
+        del rows_t
+        mc = yp.CudaMatcher(dbc, THRESHOLD)
+        cap = max(1 << 16, 1 << int(np.ceil(np.log2(expect + 4096))))
+        out = torch.zeros((cap, 16), dtype=torch.uint8, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        nd = torch.from_numpy(needles).to(dev)
+
+        def run(algo, reps):
+            ts = []
+            for _ in range(reps):
+                cnt.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                mc.find_device(nd, q, out, cap, cnt, algo=algo)
+                b.record()
+                torch.cuda.synchronize()       # the host reads the previous launch's statistics before the next one
+                ts.append(a.elapsed_time(b))
+                if int(cnt.item()) != expect:
+                    raise SystemExit(f"bench.py: {kind} haystack, algo {algo}: {int(cnt.item())} matches, numpy expects {expect}")
+            return ts
+
+        first = run(yp.ALGO_AUTO, 1)[0]                  # a fresh haystack: the prefix filter runs once and reports
+        run(yp.ALGO_AUTO, 2)
+        auto = run(yp.ALGO_AUTO, 24)                      # steady state, incl. the probes of the filter while in fallback
+        fallback, interval = dbc.auto_state
+        full = run(yp.ALGO_TENSOR_FULL, 4)
+        paired = run(yp.ALGO_TENSOR_PAIRED, 3)
+        pairs = rows_n * q
+        tp = lambda ms: pairs / (ms * 1e-3) / 1e12
+        res = {
+            "workload": what, "candidate_pairs_fraction": cand_frac, "matches": expect, "matches_checked_against": "numpy popcounts",
+            "auto_ms_mean": float(np.mean(auto)), "auto_ms_max": float(np.max(auto)), "auto_tpairs_per_s": tp(float(np.mean(auto))),
+            "auto_in_fallback": bool(fallback), "auto_probe_interval": interval, "first_launch_ms": first,
+            "unfiltered_ms": float(np.mean(full)), "unfiltered_tpairs_per_s": tp(float(np.mean(full))),
+            "prefix_filter_forced_ms": float(np.mean(paired)), "prefix_filter_forced_tpairs_per_s": tp(float(np.mean(paired))),
+            "auto_vs_best_forced": min(float(np.mean(full)), float(np.mean(paired))) / float(np.mean(auto)),
+        }
+        dbc.close()
+        del out, nd
+        return res
+
+    fam, sca, twi = scenario("families"), scenario("scattered"), scenario("prefix_twins")
+    return {"rows": rows_n, "needles": q, "threshold": THRESHOLD, "families": fam, "scattered": sca, "prefix_twins": twi,
+            "tpairs_per_s": min(fam["auto_tpairs_per_s"], sca["auto_tpairs_per_s"], twi["auto_tpairs_per_s"]),
+            "fallback_rule": "15 ns x flagged accumulator batches - 115 ns x matches > 3.3e-5 ns x pairs and flagged > 3 % of "
+                             "the batches (MatchStats, yume_pdq_b200/csrc/common.cuh)"}
 
 
 PARITY_ROWS = 200_000

@@ -160,10 +160,13 @@ int yume_pdq_cuda_db_create_synthetic(int device, size_t n_rows, uint64_t global
 int yume_pdq_cuda_db_destroy(YumePDQ_CudaDb *db);
 size_t yume_pdq_cuda_db_len(const YumePDQ_CudaDb *db);
 int yume_pdq_cuda_db_device(const YumePDQ_CudaDb *db);
-/* device pointer of the resident rows (n_rows x 32 bytes, AoS) */
 /* Device pointers to the two planes the haystack is stored as: prefix[r] = bytes 0..15 of row r, suffix[r] = bytes
  * 16..31 (n_rows x 16 B each).  Prefix filters stream the first plane only. */
 int yume_pdq_cuda_db_planes(const YumePDQ_CudaDb *db, const uint8_t **prefix, const uint8_t **suffix);
+/* ALGO_AUTO's data-dependent state for this haystack (large needle batches at threshold <= 36): *fallback = 1 while
+ * launches run the unfiltered tensor kernel because the prefix filter met too many candidates (near-duplicate
+ * families); *probe_interval = launches between probes of the filter on a slice of the rows.  Diagnostic only. */
+int yume_pdq_cuda_db_auto_state(const YumePDQ_CudaDb *db, int *fallback, uint32_t *probe_interval);
 /* overwrite rows [first, first+n) (host or device source) -- used by tests to plant */
 int yume_pdq_cuda_db_write_rows(YumePDQ_CudaDb *db, size_t first_local_row, const uint8_t *rows,
                                 size_t n);
@@ -178,6 +181,7 @@ int yume_pdq_cuda_db_write_rows(YumePDQ_CudaDb *db, size_t first_local_row, cons
 #define YUME_PDQ_CUDA_ALGO_TENSOR_FULL 6    /* kind::mxf4, always the full 256-bit dot product (threshold <= 127) */
 #define YUME_PDQ_CUDA_ALGO_TENSOR_PREFIX 7  /* kind::mxf4, always the 128-bit prefix filter (threshold <= 63) */
 #define YUME_PDQ_CUDA_ALGO_TENSOR_PAIRED 8  /* kind::mxf4, 128-bit prefix filter with two rows per f32 accumulator (s16x2 fields; threshold <= 60) */
+#define YUME_PDQ_CUDA_ALGO_TENSOR_ROWS 9    /* kind::mxf4 with the database rows in the M dimension (operand A in tensor memory): 1 .. 32 needles, 128-bit prefix filter + exact check */
 
 /* PDQMatcher::scan (matching/mod.rs:72-79): *matched = 1 iff any needle is within
  * `threshold` (inclusive) of any row.  needles q x 32 bytes, host or device. */

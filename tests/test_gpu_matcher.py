@@ -39,7 +39,8 @@ def test_planted_vs_oracle_all_algos(cuda, oracle, n_rows, q):
     assert m.scan(needles) == (len(want) > 0)
     assert m.find_min(needles) == oracle.matcher_find_min(rows, needles, 31)
     for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8,
-                 cuda.ALGO_TENSOR_FULL, cuda.ALGO_TENSOR_PREFIX, cuda.ALGO_TENSOR_PAIRED):
+                 cuda.ALGO_TENSOR_FULL, cuda.ALGO_TENSOR_PREFIX, cuda.ALGO_TENSOR_PAIRED) + (
+                     (cuda.ALGO_TENSOR_ROWS,) if q <= 32 else ()):
         assert _find_device(cuda, m, needles, algo) == sorted(want), algo
     db.close()
 
@@ -71,6 +72,8 @@ def test_thresholds(cuda, oracle, threshold):
             assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_PREFIX, cap=1 << 18) == sorted(want)
         if threshold <= 60:
             assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_PAIRED, cap=1 << 18) == sorted(want)
+        if threshold <= 128:
+            assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_ROWS, cap=1 << 18) == sorted(want)
     db.close()
     # the forced variants reject thresholds they cannot represent instead of answering wrongly
     if threshold > 127:
@@ -164,6 +167,11 @@ def test_prefix_filter_boundaries(cuda, oracle, q):
     m = cuda.CudaMatcher(db, 31)
     for algo in (cuda.ALGO_TENSOR_PREFIX, cuda.ALGO_TENSOR_PAIRED, cuda.ALGO_TENSOR_FULL, cuda.ALGO_TENSOR, cuda.ALGO_AUTO):
         assert _find_device(cuda, m, needles, algo) == want, algo
+    if q <= 32:
+        assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_ROWS) == want
+        for thr in (0, 15, 36, 37, 50, 63):
+            w = sorted(match_tuples(oracle.matcher_find(rows, needles, thr)))
+            assert _find_device(cuda, cuda.CudaMatcher(db, thr), needles, cuda.ALGO_TENSOR_ROWS, cap=1 << 18) == w, thr
     for thr in (0, 15, 36, 37, 50, 63):
         mt = cuda.CudaMatcher(db, thr)
         w = sorted(match_tuples(oracle.matcher_find(rows, needles, thr)))
@@ -378,9 +386,104 @@ def test_headline_config_10m(cuda, oracle):
     assert match_tuples(m.find_all(needles)) == want
     assert m.find_min(needles) == (want[0][0], want[0][1])
     for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8,
-                 cuda.ALGO_TENSOR_FULL, cuda.ALGO_TENSOR_PREFIX, cuda.ALGO_TENSOR_PAIRED):
+                 cuda.ALGO_TENSOR_FULL, cuda.ALGO_TENSOR_PREFIX, cuda.ALGO_TENSOR_PAIRED, cuda.ALGO_TENSOR_ROWS):
         assert _find_device(cuda, m, needles, algo) == want
     # last rows of the last chunk are planted too (tail handling)
     db.write_rows(n - 1, needles[5][None])
     assert match_tuples(m.find_all(needles))[-1] == (n - 1, 5, 0)
+    db.close()
+
+
+def _prefix_twins(rng, n_rows, q, n_twins, n_matches, oracle):
+    """A haystack the prefix filter is bad at: n_twins rows share the first 128 bits (within 0..31 bits) with one of q
+    random needles but not the rest -- candidates that are not matches -- plus n_matches true near-duplicates."""
+    needles = rng.integers(0, 256, size=(q, 32), dtype=np.uint8)
+    rows = oracle.synth_db(n_rows, first_row=5)
+    where = rng.choice(n_rows, size=n_twins + n_matches, replace=False)
+    for k, r in enumerate(where):
+        n = needles[int(rng.integers(0, q))]
+        if k < n_twins:
+            rows[r, :16] = _flip_in(n, int(rng.integers(0, 32)), 0, rng)[:16]        # the suffix stays random
+        else:
+            rows[r] = flip_bits(n, int(rng.integers(0, 34)), rng)
+    return rows, needles
+
+
+def _clustered(rng, n_rows, q, n_near, oracle):
+    """A near-duplicate family: q needles within 6 bits of one base hash (consecutive frames of a video) and n_near
+    rows within 0..40 bits of it, scattered through an otherwise random haystack."""
+    base = rng.integers(0, 256, size=32, dtype=np.uint8)
+    needles = np.stack([flip_bits(base, int(rng.integers(0, 7)), rng) for _ in range(q)])
+    rows = oracle.synth_db(n_rows, first_row=5)
+    for r in rng.choice(n_rows, size=n_near, replace=False):
+        rows[r] = flip_bits(base, int(rng.integers(0, 41)), rng)
+    return rows, needles
+
+
+def _find_device_np(cuda, matcher, needles_dev, q, algo, cap):
+    """sorted (row, needle, dist) as one structured array -- for match sets too large for Python tuples"""
+    import torch
+    out = torch.zeros((cap, 16), dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    matcher.find_device(needles_dev, q, out, cap, cnt, algo=algo)
+    torch.cuda.synchronize()
+    n = int(cnt.item())
+    assert n <= cap
+    return np.sort(out[:n].cpu().numpy().view(cuda.MATCH_DTYPE).reshape(-1), order=["row", "needle"])
+
+
+def test_auto_falls_back_on_dense_haystack(cuda, oracle):
+    """ALGO_AUTO on a haystack full of prefix twins: the first large-batch launch runs the prefix
+    filter and reports how many accumulator batches flagged and how many matches they held; from the next launch on the
+    unfiltered tensor kernel runs (fallback), probes of the filter on a slice keep it there, and a batch of unrelated
+    needles brings the filter back.  Every launch returns the oracle's match set."""
+    import torch
+    rng = np.random.default_rng(77)
+    n_rows, q = 400_000, 1024
+    rows, needles = _prefix_twins(rng, n_rows, q, 40_000, 300, oracle)
+    want = np.sort(oracle.matcher_find(rows, needles, 31), order=["row", "needle"])
+    assert 200 < len(want) < 400
+    db = cuda.CudaVectorDatabase(rows)
+    m = cuda.CudaMatcher(db, 31)
+    cap = 1 << 16
+    nd = torch.from_numpy(needles).cuda()
+    find = lambda dev, algo=cuda.ALGO_AUTO: _find_device_np(cuda, m, dev, q, algo, cap)
+    assert db.auto_state == (False, 0)
+    assert np.array_equal(find(nd), want)                   # prefix filter; leaves its statistics
+    assert db.auto_state[0] is False
+    assert np.array_equal(find(nd), want)                   # sees them: unfiltered from here on
+    assert db.auto_state == (True, 8)
+    for _ in range(18):                                     # the probes at launches 8 and 16 find dense slices
+        assert np.array_equal(find(nd), want)
+    fb, interval = db.auto_state
+    assert fb and interval >= 16
+    sparse = rng.integers(0, 256, size=(q, 32), dtype=np.uint8)
+    want_sparse = np.sort(oracle.matcher_find(rows, sparse, 31), order=["row", "needle"])
+    sd = torch.from_numpy(sparse).cuda()
+    for _ in range(2 * interval + 2):
+        assert np.array_equal(find(sd), want_sparse)
+    assert db.auto_state[0] is False                        # a sparse probe ended the fallback
+    for algo in (cuda.ALGO_TENSOR_PAIRED, cuda.ALGO_TENSOR_FULL, cuda.ALGO_TILED):
+        assert np.array_equal(find(nd, algo), want)
+    db.close()
+
+
+def test_auto_keeps_the_filter_on_near_duplicate_families(cuda, oracle):
+    """A video's 1024 near-identical frames against rows near them: 1e-3 of the pairs are candidates, nearly all of them
+    matches.  All needles of a tile flag the same accumulator column, and the unfiltered kernel would pay for every match:
+    ALGO_AUTO must stay on the prefix filter (measured 28e12 vs 10.5e12 pairs/s at 10M rows, profiles/r02y)."""
+    import torch
+    rng = np.random.default_rng(78)
+    n_rows, q = 400_000, 1024
+    rows, needles = _clustered(rng, n_rows, q, 600, oracle)
+    want = np.sort(oracle.matcher_find(rows, needles, 31), order=["row", "needle"])
+    assert len(want) > 200_000
+    db = cuda.CudaVectorDatabase(rows)
+    m = cuda.CudaMatcher(db, 31)
+    nd = torch.from_numpy(needles).cuda()
+    for _ in range(4):
+        assert np.array_equal(_find_device_np(cuda, m, nd, q, cuda.ALGO_AUTO, 1 << 20), want)
+        assert db.auto_state[0] is False
+    for algo in (cuda.ALGO_TENSOR_PAIRED, cuda.ALGO_TENSOR_FULL):        # candidate-list overflow -> inline verification
+        assert np.array_equal(_find_device_np(cuda, m, nd, q, algo, 1 << 20), want)
     db.close()

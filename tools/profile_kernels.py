@@ -23,7 +23,7 @@ if "hash" in what:
     for _ in range(3):
         k.hash_batch(frames, out=outs)
     torch.cuda.synchronize()
-if {"scan", "stream", "tiled", "exact", "tensor", "tensor128", "tensor32k"} & set(what):
+if {"scan", "stream", "tiled", "exact", "tensor", "tensor128", "tensor32k", "rows8"} & set(what):
     n = (10_000_000 // 2048 + 1) * 2048
     db = yp.CudaVectorDatabase(synthetic_rows=n)
     m = yp.CudaMatcher(db, 31)
@@ -35,8 +35,8 @@ if {"scan", "stream", "tiled", "exact", "tensor", "tensor128", "tensor32k"} & se
     for _ in range(3):
         if "scan" in what:
             m.find_device(n8, 8, out, 1 << 16, cnt, algo=yp.ALGO_TILED)
-        if "stream" in what:
-            m.find_device(n8, 8, out, 1 << 16, cnt, algo=yp.ALGO_TILED)
+        if "rows8" in what:       # rows-in-M tensor scan (matcher_tc1.cu)
+            m.find_device(n8, 8, out, 1 << 16, cnt, algo=yp.ALGO_TENSOR_ROWS)
         if "exact" in what:
             m.find_device(n8, 8, out, 1 << 16, cnt, algo=yp.ALGO_EXACT)
         if "tiled" in what:

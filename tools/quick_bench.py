@@ -105,6 +105,18 @@ def main():
             print(f"[{tag}] match 10M x  32768 paired thr={thr}: median {med / 1e3:9.2f} ms  {n * 32768 / med / 1e6:8.3f} Tpairs/s")
             cnt.zero_()
         db.close()
+    if "x1" in what:   # rows-in-M tensor scan only (developer variants: YUME_PDQ_CUDA_LIB=...)
+        tag = os.path.basename(os.environ.get("YUME_PDQ_CUDA_LIB", "default"))
+        out = torch.zeros((1 << 16, 16), dtype=torch.uint8, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for n in (1_250_048, (10_000_000 // 2048 + 1) * 2048):
+            db = yp.CudaVectorDatabase(synthetic_rows=n)
+            m = yp.CudaMatcher(db, 31)
+            for q in (8, 16, 32):
+                needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
+                med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 16, cnt, algo=yp.ALGO_TENSOR_ROWS), iters=20, warm=3, flush=flush)
+                print(f"[{tag}] rows-in-M {n:9d} x {q:3d}: median {med:8.1f} us  best {best:8.1f} us  {n * 16 / med / 1e3:7.1f} GB/s (prefix plane)")
+            db.close()
     if "cross" in what:   # crossover between the tiled POPC kernel and the paired tensor kernel
         n = (10_000_000 // 2048 + 1) * 2048
         db = yp.CudaVectorDatabase(synthetic_rows=n)
@@ -121,8 +133,9 @@ def main():
         small.close()
         for q in (8, 16, 32, 64, 128, 256, 512, 1024, 2048):
             needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
-            for name, algo in (("tiled", yp.ALGO_TILED), ("paired", yp.ALGO_TENSOR_PAIRED), ("auto", yp.ALGO_AUTO)):
-                if name == "tiled" and q > 256:
+            for name, algo in (("tiled", yp.ALGO_TILED), ("paired", yp.ALGO_TENSOR_PAIRED), ("rows", yp.ALGO_TENSOR_ROWS),
+                               ("auto", yp.ALGO_AUTO)):
+                if (name == "tiled" and q > 256) or (name == "rows" and q > 32):
                     continue
                 med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 20, cnt, algo=algo), iters=10, warm=2, flush=flush)
                 print(f"cross 10M x {q:4d} {name:6s}: median {med:9.1f} us  best {best:9.1f} us  {n * q / med / 1e6:8.3f} Tpairs/s  "
@@ -135,10 +148,10 @@ def main():
         for n in (960 * 148, 960 * 148 * 4, 960 * 148 * 16, 1_250_048, 10_000_384):
             db = yp.CudaVectorDatabase(synthetic_rows=n)
             m = yp.CudaMatcher(db, 31)
-            for q in (8, 128, 1024):
+            for q in (8, 32, 128, 1024):
                 needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
-                for name, algo in (("tiled", yp.ALGO_TILED), ("paired", yp.ALGO_TENSOR_PAIRED)):
-                    if name == "tiled" and q > 128:
+                for name, algo in (("tiled", yp.ALGO_TILED), ("paired", yp.ALGO_TENSOR_PAIRED), ("rows", yp.ALGO_TENSOR_ROWS)):
+                    if (name == "tiled" and q > 128) or (name == "rows" and q > 32):
                         continue
                     med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 20, cnt, algo=algo), iters=20, warm=3, flush=flush)
                     print(f"fixed {n:9d} rows x {q:4d} {name:6s}: median {med:8.1f} us  best {best:8.1f} us")

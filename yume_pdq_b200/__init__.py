@@ -29,7 +29,7 @@ LIB_PATH = os.environ.get("YUME_PDQ_CUDA_LIB") or os.path.join(HERE, "libyume_pd
 MATCH_DTYPE = np.dtype([("row", "<u8"), ("needle", "<u4"), ("dist", "<u4")])
 
 ALGO_AUTO, ALGO_EXACT, ALGO_TILED, ALGO_TENSOR, ALGO_TENSOR_I8 = 0, 1, 2, 4, 5
-ALGO_TENSOR_FULL, ALGO_TENSOR_PREFIX, ALGO_TENSOR_PAIRED = 6, 7, 8
+ALGO_TENSOR_FULL, ALGO_TENSOR_PREFIX, ALGO_TENSOR_PAIRED, ALGO_TENSOR_ROWS = 6, 7, 8, 9
 
 OP_T = 0
 OP_NEGATE_ALT_COLS_FALSE = 1
@@ -98,6 +98,7 @@ SIGNATURES = {
     "yume_pdq_cuda_db_len": (C.c_size_t, [_vp]),
     "yume_pdq_cuda_db_device": (C.c_int, [_vp]),
     "yume_pdq_cuda_db_planes": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "yume_pdq_cuda_db_auto_state": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_uint32)]),
     "yume_pdq_cuda_db_write_rows": (C.c_int, [_vp, C.c_size_t, _vp, C.c_size_t]),
     "yume_pdq_cuda_matcher_scan": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, C.POINTER(C.c_int), _vp]),
     "yume_pdq_cuda_matcher_find": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _vp, C.c_size_t,
@@ -442,6 +443,14 @@ class CudaVectorDatabase:
         pre, suf = _vp(), _vp()
         _check(lib.yume_pdq_cuda_db_planes(self._h, C.byref(pre), C.byref(suf)), "db_planes")
         return int(pre.value or 0), int(suf.value or 0)
+
+    @property
+    def auto_state(self) -> tuple[bool, int]:
+        """(fallback, probe_interval) of ALGO_AUTO on this haystack: fallback is True while large needle batches run the
+        unfiltered tensor kernel because the prefix filter met too many candidates."""
+        fb, iv = C.c_int(0), C.c_uint32(0)
+        _check(lib.yume_pdq_cuda_db_auto_state(self._h, C.byref(fb), C.byref(iv)), "db_auto_state")
+        return bool(fb.value), int(iv.value)
 
     def write_rows(self, first_local_row: int, rows):
         if isinstance(rows, np.ndarray):

@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, "libyume_pdq_cuda.so")
 LIB_ALIAS = os.path.join(HERE, "libyume_pdq.so")
 CLI_SRC = os.path.join(HERE, "cli")
 CLI = os.path.join(HERE, "yume-pdq-cuda")     # `pipe` front end (cli/yume_pdq_pipe.cpp), links only the C ABI
-SOURCES = ["api.cu", "hasher.cu", "matcher.cu", "matcher_tc.cu", "matcher_tc4.cu", "matcher_tc4x2.cu", "synth.cu", "peak.cu"]
+SOURCES = ["api.cu", "hasher.cu", "matcher.cu", "matcher_tc.cu", "matcher_tc4.cu", "matcher_tc4x2.cu", "matcher_tc1.cu", "synth.cu", "peak.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--shared",

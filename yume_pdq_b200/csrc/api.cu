@@ -755,9 +755,11 @@ static int db_alloc(int device, size_t n_rows, uint64_t offset, YumePDQ_CudaDb *
     cudaDeviceGetAttribute(&db->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaError_t e = cudaMalloc(&db->rows, std::max<size_t>(n_rows * 32, 256));
     if (e == cudaSuccess)
-        e = cudaMalloc(&db->d_count, 16);
+        e = cudaMalloc(&db->d_count, 32);     // count, pad, min key; [4]: match counter of ALGO_AUTO's probes
     if (e == cudaSuccess)
-        e = cudaMallocHost(&db->h_pin, 64);
+        e = cudaMallocHost(&db->h_pin, 16 + sizeof(ypdq::MatchStats) + 64);
+    if (e == cudaSuccess)
+        e = cudaMemset(db->d_count, 0, 32);
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         yume_pdq_cuda_db_destroy(db);
@@ -765,6 +767,7 @@ static int db_alloc(int device, size_t n_rows, uint64_t offset, YumePDQ_CudaDb *
     }
     db->d_min = reinterpret_cast<unsigned long long *>(db->d_count + 2);
     db->stats = new (static_cast<uint8_t *>(db->h_pin) + 16) ypdq::MatchStats();
+    db->stats->probe_count = db->d_count + 4;
     *out = db;
     return 0;
 }
@@ -854,6 +857,17 @@ int yume_pdq_cuda_db_planes(const YumePDQ_CudaDb *db, const uint8_t **prefix, co
         return YUME_PDQ_CUDA_E_INVALID;
     *prefix = db->rows;
     *suffix = db->rows + db->n_rows * 16;
+    return 0;
+}
+
+int yume_pdq_cuda_db_auto_state(const YumePDQ_CudaDb *db, int *fallback, uint32_t *probe_interval)
+{
+    if (!db || !db->stats)
+        return YUME_PDQ_CUDA_E_INVALID;
+    if (fallback)
+        *fallback = (int)db->stats->fallback;
+    if (probe_interval)
+        *probe_interval = db->stats->probe_interval;
     return 0;
 }
 

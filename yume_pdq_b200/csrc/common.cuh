@@ -81,18 +81,31 @@ struct DbPlanes {
 
 // What the prefix-filter matcher observed on a haystack: written by the device (pinned, mapped memory) at the end
 // of a paired-tensor launch, read by the host when it picks the kernel for the NEXT launch on the same haystack.
-// Random rows pass the 128/122-bit prefix filter at 2e-8 of the pairs (threshold 31); a database of near-duplicate
-// families matched against a video's near-identical frames passes 1e-5 and more, and every candidate costs the
-// paired kernel ~13 ns -- past 2.3e-6 the unfiltered 256-bit tensor kernel (14.8e12 pairs/s) is faster.
+// Measured on a B200, 32768 needles x 10M rows (profiles/r02y, r02p):
+//  * what the filter pays for is not a candidate but an accumulator BATCH (one epilogue warp's 80 columns x 32 needles
+//    = 5120 pairs) that holds at least one and takes the rare path: 5 .. 26 ns of kernel time each (random rows at
+//    threshold 36: 2e5 flagged batches, 16.1 ms instead of 10.8; at threshold 40: 5.6e6, 96 ms).  A near-duplicate FAMILY
+//    (1024 frames of a video against 10,000 rows near them: 1e7 candidates) flags only 3e5 batches -- all needles of a
+//    tile flag the same column at once -- and runs in 11.7 ms;
+//  * the unfiltered 256-bit kernel takes twice the time on random rows (14.8e12 pairs/s) and pays ~115 ns per MATCH:
+//    780,000 scattered matches take 112 ms where the filter takes 16 ms.
+// So the unfiltered kernel is the better choice only when many batches flag AND few of their candidates are matches
+// (high thresholds; rows that share a prefix with the needles but not the rest):
+//     15 ns x flagged - 115 ns x matches  >  3.3e-5 ns x pairs     and     flagged > 3 % of the batches
+// (below ~3 % the pipeline's slack absorbs most of a flagged batch: 1e6 scattered ones cost 5 ms, not 15).
 struct MatchStats {
     // device-written (one launch at a time per haystack: the host-facing calls hold the handle's mutex)
-    volatile unsigned long long candidates;
-    volatile unsigned long long pairs;
+    volatile unsigned long long flagged;   // accumulator batches that took the rare path
+    volatile unsigned long long matches;   // matches among the listed candidates
+    volatile unsigned long long pairs;     // 0: no result since the host last cleared it
     // host-only: adaptive state of ALGO_AUTO
-    uint32_t fallback_left;      // launches to run unfiltered before the filter is probed again
-    uint32_t fallback_interval;  // doubles while the probes keep finding a dense haystack (8 .. 256)
+    uint32_t fallback;           // 1: launches run unfiltered; the filter is only probed on a slice of the rows
+    uint32_t probe_interval;     // launches between probes while in fallback (8, 16 .. 64)
+    uint32_t since_probe;
+    uint32_t probe_seq;          // moves the probed slice through the haystack
+    uint32_t *probe_count;       // device: match counter of the probes (their matches are discarded)
 };
-constexpr double kPrefixFilterBreakEven = 2.3e-6;   // candidates per pair
+constexpr double kFlaggedBatchNs = 15.0, kUnfilteredMatchNs = 115.0, kUnfilteredExtraNsPerPair = 3.3e-5, kFlaggedBatchFraction = 0.03;
 
 enum MatchMode : int { MODE_LIST = 0, MODE_MIN = 1 };
 
@@ -128,6 +141,11 @@ int launch_match_tensor4x2(DbPlanes rows, size_t n_rows, uint64_t row_offset, co
                            size_t q, uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
                            unsigned long long *min_key, int mode, int sm_count, cudaStream_t s,
                            uint32_t needle_base = 0, MatchStats *stats = nullptr);
+
+// 1 .. 32 needles: database rows in the M dimension, operand A written to tensor memory from registers (matcher_tc1.cu)
+int launch_match_tensor_rows(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles, size_t q,
+                             uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
+                             unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base = 0);
 
 int launch_synth_frames(float *frames, size_t n, uint64_t first, uint64_t seed, int kind,
                         cudaStream_t s);

@@ -274,39 +274,58 @@ int launch_match(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_
     Sink sink{out, cap, count, min_key, row_offset, (uint64_t)q, mode, needle_base};
     const uint4 *needles4 = reinterpret_cast<const uint4 *>(needles);
     if (algo == YUME_PDQ_CUDA_ALGO_AUTO) {
-        // Measured on B200 (10M rows, threshold 31; profiles/r02*/quick.log): tiled POPC kernel 54 us for 8 needles, 86 us
-        // for 16, 157 us for 32 (2.1e12 pairs/s from there on); paired tensor kernel 74..86 us for anything up to 128
-        // needles (one launch, X2One), 142 us for 256, 230 us for 512, 0.39 ms for 1024.  Above threshold 36 the tensor
-        // path is the unpaired full kernel (1024 needles 0.8 ms vs tiled 4.7 ms); the 96-bit prefix bound of the POPC
-        // kernels stops filtering once the threshold approaches 48.
-        // (a persistent tensor launch costs ~12 us before the first row: not for tiny shards)
-        if (q >= (threshold <= 36 ? 14u : 512u) && (q >= 512 || n_rows >= 100000))
+        // Measured on B200 (10M rows, threshold 31; profiles/r02*/quick.log): tiled POPC kernel 53 us for 8 needles, 86 us
+        // for 16, 157 us for 32 (2.1e12 pairs/s from there on); rows-in-M tensor kernel 45 us up to 8 needles, 53 us up to
+        // 16; needles-in-M (paired) tensor kernel 74..86 us for anything up to 128 needles (one launch, X2One), 142 us for
+        // 256, 230 us for 512, 0.39 ms for 1024.  Above threshold 36 the tensor path is the unpaired full kernel (1024
+        // needles 0.8 ms vs tiled 4.7 ms); the 96-bit prefix bound of the POPC kernels stops filtering once the threshold
+        // approaches 48.  A persistent tensor launch costs ~12 us before the first row: small shards stay on the POPC
+        // kernel (1.25M rows x 8: 14.4 us either way).
+        if (q <= 16 && threshold <= 40 && n_rows >= 2000000)
+            algo = YUME_PDQ_CUDA_ALGO_TENSOR_ROWS;
+        else if (q >= (threshold <= 36 ? 14u : 512u) && (q >= 512 || n_rows >= 100000))
             algo = YUME_PDQ_CUDA_ALGO_TENSOR;
         else if (threshold > 40)
             algo = YUME_PDQ_CUDA_ALGO_EXACT;
         else
             algo = YUME_PDQ_CUDA_ALGO_TILED;
-        // Data-dependent part (threshold <= 36, >= 512 needles): the paired prefix filter is only the faster tensor
-        // kernel while candidates are rare.  The previous launch on this haystack left its candidate rate in `stats`;
-        // past the break-even the next launches run the unfiltered 256-bit kernel, and the filter is probed again
-        // after 8, 16, ... 256 launches (back to 8 as soon as a probe finds the haystack sparse).
+        // Data-dependent part (threshold <= 36, >= 512 needles): the paired prefix filter is the faster tensor kernel
+        // unless many accumulator batches flag and few of their candidates are matches (MatchStats, common.cuh).  Every
+        // paired launch leaves its counts in `stats` (mapped host memory).  Once a launch is past the break-even the
+        // haystack is in FALLBACK: launches run the unfiltered 256-bit kernel, and every 8th .. 64th of them also runs
+        // the filter on 1/64 of the rows (a slice that moves through the haystack; its matches are discarded) -- a slice
+        // past the break-even doubles the interval, any other ends the fallback.
         if (algo == YUME_PDQ_CUDA_ALGO_TENSOR && threshold <= 36 && q >= 512 && stats) {
-            const unsigned long long pairs_seen = stats->pairs, cand_seen = stats->candidates;
-            const bool dense = pairs_seen > 0 && (double)cand_seen > kPrefixFilterBreakEven * (double)pairs_seen;
-            if (stats->fallback_left > 0) {
-                stats->fallback_left--;
+            const unsigned long long pairs_seen = stats->pairs;
+            if (pairs_seen > 0) {
+                const double flagged = (double)stats->flagged, matches = (double)stats->matches, pairs = (double)pairs_seen;
+                const bool dense = flagged > kFlaggedBatchFraction * pairs / 5120.0 &&
+                                   kFlaggedBatchNs * flagged - kUnfilteredMatchNs * matches > kUnfilteredExtraNsPerPair * pairs;
+                stats->pairs = 0;
+                if (dense) {
+                    stats->probe_interval = stats->fallback ? std::min<uint32_t>(stats->probe_interval * 2, 64) : 8;
+                    stats->fallback = 1;
+                } else {
+                    stats->fallback = 0;
+                }
+            }
+            if (stats->fallback) {
                 algo = YUME_PDQ_CUDA_ALGO_TENSOR_FULL;
-            } else if (dense) {
-                stats->fallback_interval = std::min<uint32_t>(std::max<uint32_t>(stats->fallback_interval * 2, 8), 256);
-                stats->fallback_left = stats->fallback_interval - 1;
-                stats->pairs = 0;          // the next probe's result decides again
-                stats->candidates = 0;
-                algo = YUME_PDQ_CUDA_ALGO_TENSOR_FULL;
-            } else {
-                stats->fallback_interval = 0;
+                const size_t slice = std::min<size_t>(n_rows, std::max<size_t>(n_rows / 64, (size_t)960 * sm_count));
+                if (++stats->since_probe >= stats->probe_interval && stats->probe_count && slice < n_rows) {
+                    stats->since_probe = 0;
+                    const size_t first = (size_t)((stats->probe_seq++ * 0x9E3779B97F4A7C15ull) % (n_rows - slice + 1));
+                    int rc = launch_match_tensor4x2(DbPlanes{rows.pre + first, rows.suf + first}, slice, 0, needles, q, threshold,
+                                                    nullptr, 0, stats->probe_count, nullptr, MODE_LIST, sm_count, s, 0, stats);
+                    if (rc)
+                        return rc;
+                }
             }
         }
     }
+    if (algo == YUME_PDQ_CUDA_ALGO_TENSOR_ROWS)
+        return launch_match_tensor_rows(rows, n_rows, row_offset, needles, q, threshold, out, cap, count, min_key, mode,
+                                        sm_count, s, needle_base);
     // candidates of the 128-bit prefix filter: 4.6e-9 of the random pairs at threshold 31, 6e-7 at 36, 1.7e-5 at 40
     if (algo == YUME_PDQ_CUDA_ALGO_TENSOR_PAIRED || (algo == YUME_PDQ_CUDA_ALGO_TENSOR && threshold <= 36))
         return launch_match_tensor4x2(rows, n_rows, row_offset, needles, q, threshold, out, cap, count, min_key,

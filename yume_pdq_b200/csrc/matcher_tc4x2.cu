@@ -243,16 +243,18 @@ struct X2Candidate {
 constexpr uint32_t X2_CAND_SLOTS = X2_CAND_SLOTS_CFG;   // per epilogue warp
 struct X2CandList {
     X2Candidate *items;     // [gridDim.x * X2_EPI_WARPS][X2_CAND_SLOTS]
-    uint32_t *counts;       // [gridDim.x * X2_EPI_WARPS]
+    uint32_t *counts;       // [gridDim.x * X2_EPI_WARPS] candidates, then as many counts of flagged accumulator batches
+    uint32_t n_regions;
 };
 
-__device__ __forceinline__ void x2_verify(uint64_t row, uint32_t needle, const DbPlanes &rows, const Tc4Sink &sink)
+__device__ __forceinline__ bool x2_verify(uint64_t row, uint32_t needle, const DbPlanes &rows, const Tc4Sink &sink)
 {
     const uint4 b0 = __ldg(sink.needles_raw + 2 * (size_t)needle), b1 = __ldg(sink.needles_raw + 2 * (size_t)needle + 1);
     const uint4 a0 = __ldg(rows.pre + row), a1 = __ldg(rows.suf + row);
     const uint32_t dist = hamming256(a0, a1, b0, b1);
     if (dist <= sink.threshold)
         tc4_emit(sink, row, needle, dist);
+    return dist <= sink.threshold;
 }
 
 // rare path, entered by the whole warp: both rows of every flagged column of every lane become candidates
@@ -300,23 +302,33 @@ __device__ __forceinline__ void x2_report(const int32_t (&v)[W], int32_t lo_min,
     }
 }
 
-// one CTA per candidate region (= epilogue warp of the scan); also leaves the launch's candidate total for the host
+// one CTA per candidate region (= epilogue warp of the scan); also leaves the launch's count of flagged batches for the host
 __global__ void __launch_bounds__(128)
 verify_candidates_kernel(DbPlanes rows, X2CandList cand, Tc4Sink sink, MatchStats *stats, unsigned long long pairs,
-                         unsigned long long *tally /* device: {sum of counts, CTAs done}, zeroed */)
+                         unsigned long long *tally /* device: {flagged batches, matches, CTAs done}, zeroed */)
 {
-    if (stats && threadIdx.x == 0) {
-        atomicAdd(&tally[0], (unsigned long long)cand.counts[blockIdx.x]);
-        __threadfence();
-        if (atomicAdd(&tally[1], 1ull) == gridDim.x - 1) {     // last CTA: plain stores into the mapped host struct
-            stats->candidates = atomicAdd(&tally[0], 0ull);
-            stats->pairs = pairs;
-        }
-    }
     const uint32_t n = min(cand.counts[blockIdx.x], X2_CAND_SLOTS);
     const X2Candidate *region = cand.items + (size_t)blockIdx.x * X2_CAND_SLOTS;
+    uint32_t hits = 0;
     for (uint32_t i = threadIdx.x; i < n; i += 128)
-        x2_verify(region[i].row, region[i].needle, rows, sink);
+        hits += x2_verify(region[i].row, region[i].needle, rows, sink);
+    if (stats) {
+        // statistics of the launch for ALGO_AUTO (matches verified inline after a list overflow are not counted)
+        hits = __reduce_add_sync(0xFFFFFFFFu, hits);
+        if ((threadIdx.x & 31) == 0 && hits)
+            atomicAdd(&tally[1], (unsigned long long)hits);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            atomicAdd(&tally[0], (unsigned long long)cand.counts[cand.n_regions + blockIdx.x]);
+            __threadfence();
+            if (atomicAdd(&tally[2], 1ull) == gridDim.x - 1) {     // last CTA: plain stores into the mapped host struct
+                stats->flagged = atomicAdd(&tally[0], 0ull);
+                stats->matches = atomicAdd(&tally[1], 0ull);
+                __threadfence_system();
+                stats->pairs = pairs;
+            }
+        }
+    }
 }
 
 // Work units (super-tile, needle tile range), dealt round-robin to the CTAs in chunk-major order.  Every role of a
@@ -383,7 +395,7 @@ __device__ __forceinline__ void x2_epilogue(uint32_t tmem, uint32_t quad, uint32
     }
     const uint32_t region_id = blockIdx.x * Cfg::EPI_WARPS + part * 4 + quad;
     X2Candidate *region = cand.items + (size_t)region_id * X2_CAND_SLOTS;
-    uint32_t n_cand = 0;
+    uint32_t n_cand = 0, n_flagged = 0;      // candidates listed / accumulator batches that took the rare path
     int32_t v[X2_EB];
     uint32_t parity = 0;
 #ifdef X2_TRACE
@@ -416,6 +428,7 @@ __device__ __forceinline__ void x2_epilogue(uint32_t tmem, uint32_t quad, uint32
                     // rare path; opaque copies keep the 64-bit row arithmetic out of the hot loop
                     uint32_t m_ = m;
                     asm volatile("" : "+r"(m_));
+                    n_flagged++;
                     const uint32_t needle = m_ * X2_M + quad * 32 + lane;
                     x2_report<X2_EB>(v, lmin, hmin, st * X2_ROWS + acc * (2 * X2_N) + part * X2_EB, n_rows, needle,
                                      needle < q, lane, rows, sink, region, n_cand);
@@ -434,6 +447,7 @@ __device__ __forceinline__ void x2_epilogue(uint32_t tmem, uint32_t quad, uint32
             x2_verify(region[i].row, region[i].needle, rows, sink);
     } else if (lane == 0) {
         cand.counts[region_id] = n_cand;
+        cand.counts[cand.n_regions + region_id] = n_flagged;
     }
 }
 
@@ -692,15 +706,15 @@ int launch_match_tensor4x2(DbPlanes rows, size_t n_rows, uint64_t row_offset, co
     const size_t tile_bytes = one ? 0 : (size_t)n_mtiles * X2_A_BYTES;
     const size_t exp_bytes = tile_bytes + (one ? 0 : (size_t)n_mtiles * X2_M * sizeof(int2));
     const bool small = n_mtiles <= X2_SMALL_MAX_TILES;
-    const size_t n_regions = (size_t)grid * (small ? X2Small::EPI_WARPS : X2Large::EPI_WARPS), count_bytes = (n_regions * 4 + 255) / 256 * 256;
+    const size_t n_regions = (size_t)grid * (small ? X2Small::EPI_WARPS : X2Large::EPI_WARPS), count_bytes = (2 * n_regions * 4 + 255) / 256 * 256;
     uint8_t *exp = nullptr;
     const size_t scratch_bytes = exp_bytes + count_bytes + n_regions * X2_CAND_SLOTS * sizeof(X2Candidate);
-    cudaError_t e = cudaMallocAsync(&exp, scratch_bytes + 16, s);
+    cudaError_t e = cudaMallocAsync(&exp, scratch_bytes + 32, s);
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         return e == cudaErrorMemoryAllocation ? YUME_PDQ_CUDA_E_NOMEM : (int)e;
     }
-    X2CandList cand{reinterpret_cast<X2Candidate *>(exp + exp_bytes + count_bytes), reinterpret_cast<uint32_t *>(exp + exp_bytes)};
+    X2CandList cand{reinterpret_cast<X2Candidate *>(exp + exp_bytes + count_bytes), reinterpret_cast<uint32_t *>(exp + exp_bytes), (uint32_t)n_regions};
     int2 *mins = reinterpret_cast<int2 *>(exp + tile_bytes);
     if (one) {
         static_assert(X2One::THREADS == X2Small::THREADS && X2One::EPI_WARPS == X2Small::EPI_WARPS, "same launch shape");
@@ -730,7 +744,7 @@ int launch_match_tensor4x2(DbPlanes rows, size_t n_rows, uint64_t row_offset, co
     YPDQ_LAUNCH_CHECK();
     unsigned long long *tally = reinterpret_cast<unsigned long long *>(exp + scratch_bytes);
     if (stats)
-        YPDQ_CUDA_TRY(cudaMemsetAsync(tally, 0, 16, s));
+        YPDQ_CUDA_TRY(cudaMemsetAsync(tally, 0, 24, s));
     verify_candidates_kernel<<<(unsigned)n_regions, 128, 0, s>>>(rows, cand, sink, stats, (unsigned long long)n_rows * q, tally);
     YPDQ_LAUNCH_CHECK();
     YPDQ_CUDA_TRY(cudaFreeAsync(exp, s));
