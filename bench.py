@@ -471,7 +471,7 @@ def main():
     n8 = nd[:8].contiguous()
     s_mean, s_med, s_min = time_kernel(
         lambda: matcher.find_device(n8, 8, match_out, CAP, match_cnt), 20, flush)
-    rows_in_m = shard_rows >= 2_000_000          # ALGO_AUTO's rule for <= 16 needles at threshold <= 40 (matcher.cu)
+    rows_in_m = shard_rows >= 1_000_000          # ALGO_AUTO's rule for <= 8 needles at threshold <= 40 (matcher.cu)
     p_mean, _, _ = time_kernel(
         lambda: matcher.find_device(n8, 8, match_out, CAP, match_cnt, algo=yp.ALGO_TILED), 20, flush)
     # (3b) the needle counts of the reference's batched CpuMatcher<B, N> and of a 128-frame video chunk
@@ -565,11 +565,11 @@ def main():
             "db_gbs": scan_bytes / (s_mean * 1e-3) / 1e9,
             "db_gbs_note": "database bytes covered per second (32 B per row); may exceed the HBM peak because only the prefix plane is read",
             "algorithmic_bytes": shard_rows * 16, "hbm_gbs": shard_rows * 16 / (s_mean * 1e-3) / 1e9,
-            "bound": ("alu pipe (row -> e2m1 operand masking, 22 integer instructions per row) + launch latency" if rows_in_m else
+            "bound": ("alu pipe (row -> e2m1 operand masking + sign test + loop: ~60 instructions per row, ncu: 58 % busy) + ~10 us launch / ramp" if rows_in_m else
                       "xu (POPC pipe) + launch latency"), "peak": hbm_peak,
             "frac": shard_rows * 16 / (s_mean * 1e-3) / 1e9 / hbm_peak, "peak_source": peak_src,
             "popc_scan": {
-                "kernel": "match_tiled_kernel forced (ALGO_TILED): the XU-bound alternative, ALGO_AUTO's choice below 2M rows",
+                "kernel": "match_tiled_kernel forced (ALGO_TILED): the XU-bound alternative, ALGO_AUTO's choice below 1M rows",
                 "us": p_mean * 1e3, "popc_per_pair": 2, "popc_rate": 2.0 * shard_rows * 8 / (p_mean * 1e-3),
                 "popc_peak": popc_peak, "popc_frac": 2.0 * shard_rows * 8 / (p_mean * 1e-3) / popc_peak,
                 "popc_peak_source": "16 POPC / clk / SM x %d SMs x %.0f MHz (median SM clock of this run)" % (sm_count, sm_clk / 1e6)},

@@ -8,6 +8,7 @@ for what in "$@"; do
     hash)   K=hash_fused_kernel ;;
     scan)   K=match_tiled_kernel ;;
     tensor) K=match_tensor4 ;;
+    tensor32k) K=match_tensor4x2 ;;
     tensor128) K=match_tensor4x2 ;;
     rows8) K=match_rows_m ;;
     *)      K=$what ;;

@@ -18,8 +18,12 @@
 //   * the same thread reads its row's N accumulators back (one tcgen05.ld) and ANDs their bit patterns (3-input LOP3
 //     tree): sign bit clear = some needle is within the threshold on the 122 prefix bits (6e-9 of the pairs on random
 //     data at threshold 31); those pairs are verified on the packed 256 bits, so the reported set is exact.
-// Measured on a B200 (tools/x1_test.cu): the pair of small-N MMAs issues every ~100 clk (A is read from TMEM at
-// 4 KB per MMA), i.e. 0.78 clk per row and SM = 27 us for 10M rows -- the time HBM needs for the 16-byte prefix plane.
+// What bounds it (profiles/r02q/ncu_rows8_raw.csv, 10M rows x 8 needles in 41 us): the ALU pipe.  A row costs 22 integer
+// instructions of operand masking + 4 of sign test + its share of the loop (two tcgen05.ld/st, an mbarrier wait and
+// arrive, a cp.async): ~60 instructions, 80 % of them on the 64-lane ALU pipe, which ncu shows 58 % busy at an issue
+// rate of 0.54 per scheduler.  HBM would need 25 us for the 16-byte prefix plane, the tensor pipe is 5 % busy.  One
+// thread can issue a small-N MMA only every ~60 clk and a commit in ~54 (tools/x1_test.cu: a latency of the issuing
+// thread -- four issuers reach four times the rate of one), hence one issuing warp per worker group.
 //
 // Persistent kernel, one CTA per SM: G groups of 4 worker warps (warp % 4 = TMEM lane quadrant) + one MMA-issuing warp each.
 // Every worker thread streams ITS rows' 16-byte prefixes through a private ring of R cp.async copies (no producer warp,
@@ -30,6 +34,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc4_common.cuh"
@@ -80,16 +85,16 @@ struct X1Cfg {
 #define X1_G16_CFG 3
 #define X1_S16_CFG 2
 #define X1_T32_CFG 1
-#define X1_G32_CFG 3
-#define X1_S32_CFG 3
+#define X1_G32_CFG 4
+#define X1_S32_CFG 2
 #define X1_R_CFG 8
 #endif
 #ifndef X1_ISSUER_SLEEP_NS
 #define X1_ISSUER_SLEEP_NS 32
 #endif
-// Measured on a B200, 10M rows (profiles/r02x): N = 8: T2 G4 S2 45.2 us, T3 G3 S2 45.2, T2 G5 S2 47.1, T2 G3 S3 51.3,
-// T1 G5 S4 61.5; N = 16: T2 G3 S2 53.4, T1 G4 S3 63.6, T3 G2 S2 55.5; N = 32: T1 G3 S3 78, T1 G4 S2 69.7 (the needles-in-M
-// kernel does 32 needles in 77 us, so AUTO sends only <= 16 needles here).
+// Measured on a B200, 10M rows x {8, 16, 32} needles (profiles/r02y .. r03a; T tiles per unit, G groups, S slots):
+//   N = 8:  T2 G4 S2 41.0 us, T3 G3 S2 41.1, T4 G2 S2 45.1        N = 16: T2 G3 S2 45.2, T3 G2 S2 49.2, T1 G4 S3 51.2
+//   N = 32: T1 G4 S2 55.4, T1 G3 S3 59.5, T2 G2 S2 59.3           (needles-in-M kernel: 77 us for any of them)
 #ifndef X1_T8_CFG
 #define X1_T8_CFG 2
 #define X1_G8_CFG 4
@@ -335,16 +340,18 @@ match_rows_m_kernel(DbPlanes rows, uint64_t n_rows, uint32_t q, Tc4Sink sink)
 #pragma unroll 1
         for (uint32_t p = 0; p + 1 < (uint32_t)R; p++)
             fetch(p, p);
-        uint32_t s = 0, sl = 0, par_d = 0;       // accumulator slot / ring cursors, phase parity of d_full
-        // Iteration i CONSUMES unit i - S (frees accumulator slot s) and PRODUCES unit i into the same slot.  The two are
+        static_assert((R & (R - 1)) == 0, "ring depth: a power of two");
+        uint32_t sl = 0;       // ring slot of the unit being produced
+        // Iteration i CONSUMES unit i - S (frees accumulator slot i % S) and PRODUCES unit i into the same slot.  The two are
         // interleaved so that the TMEM reads of the one and the TMEM writes of the other are in flight under the other's
         // integer work: [wait d_full, issue tcgen05.ld] [rows -> 16 operand words each, issue tcgen05.st] [wait::ld,
-        // compare] [wait::st, hand the slot to the MMA warp].
-        for (uint32_t i = 0; i < n_it + S; i++) {
+        // compare] [wait::st, hand the slot to the MMA warp].  CONSUME / PRODUCE are compile-time flags: the steady-state
+        // loop below is unrolled over the S slots and carries no per-iteration conditions.
+        auto step = [&](auto CONSUME, auto PRODUCE, uint32_t i, uint32_t s, uint32_t par_d) {
+            constexpr bool consume = decltype(CONSUME)::value, produce = decltype(PRODUCE)::value;
             const uint32_t col = lane_tmem + s * Cfg::SLOT_COLS;
-            const bool consume = i >= (uint32_t)S, produce = i < n_it;
             uint32_t v[T][N];
-            if (consume) {
+            if constexpr (consume) {
                 x1_wait(dfull + 8 * s, par_d);
                 if (warp == 0 && lane == 0) X1_TR(3, i - S);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -358,17 +365,18 @@ match_rows_m_kernel(DbPlanes rows, uint64_t n_rows, uint32_t q, Tc4Sink sink)
                         T4_LD_X32(v[t], 0, col + 16 * T + N * t);
                 }
             }
-            if (produce) {
+            if constexpr (produce) {
                 if (warp == 0 && lane == 0) X1_TR(5, i);
-                fetch(i + R - 1, sl == 0 ? (uint32_t)R - 1 : sl - 1);           // refill the slot consumed one iteration ago
+                fetch(i + R - 1, (sl - 1u) & (uint32_t)(R - 1));                   // refill the slot consumed one iteration ago
                 asm volatile("cp.async.wait_group %0;" ::"n"(R - 1) : "memory");   // unit i's copies have landed
                 if (warp == 0 && lane == 0) X1_TR(6, i);
+                const uint32_t src = cell + sl * (T * CELL_STRIDE);
 #pragma unroll
                 for (int t = 0; t < T; t++) {
                     uint4 r;
                     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                                 : "r"(cell + (sl * T + t) * CELL_STRIDE)
+                                 : "r"(src + t * CELL_STRIDE)
                                  : "memory");
                     uint4 c0 = mask32(r.x);
                     c0.x = (c0.x & 0xFF000000u) | X1_ROW_BIAS;
@@ -380,10 +388,9 @@ match_rows_m_kernel(DbPlanes rows, uint64_t n_rows, uint32_t q, Tc4Sink sink)
                         "r"(c2.z), "r"(c2.w), "r"(c3.x), "r"(c3.y), "r"(c3.z), "r"(c3.w)
                         : "memory");
                 }
-                if (++sl == (uint32_t)R)
-                    sl = 0;
+                sl = (sl + 1u) & (uint32_t)(R - 1);
             }
-            if (consume) {
+            if constexpr (consume) {
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (warp == 0 && lane == 0) X1_TR(4, i - S);
                 uint32_t below = 0xFFFFFFFFu;       // sign bit survives iff every accumulator of every row is negative
@@ -405,18 +412,36 @@ match_rows_m_kernel(DbPlanes rows, uint64_t n_rows, uint32_t q, Tc4Sink sink)
                     }
                 }
             }
-            if (produce) {
+            if constexpr (produce) {
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 if (lane == 0)
                     bar_arrive_addr(afull + 8 * s);
                 if (warp == 0 && lane == 0) X1_TR(7, i);
             }
-            if (++s == (uint32_t)S) {
-                s = 0;
-                if (consume)
-                    par_d ^= 1u;
-            }
+        };
+        constexpr std::true_type yes{};
+        constexpr std::false_type no{};
+        // first round: nothing to consume yet
+#pragma unroll
+        for (uint32_t s = 0; s < (uint32_t)S; s++)
+            if (s < n_it)
+                step(no, yes, s, s, 0u);
+        // steady state: rounds in which every slot both consumes and produces
+        const uint32_t full_rounds = n_it / S;
+        for (uint32_t r = 1; r < full_rounds; r++) {
+#pragma unroll
+            for (uint32_t s = 0; s < (uint32_t)S; s++)
+                step(yes, yes, r * S + s, s, (r - 1u) & 1u);
+        }
+        // last units and the drain
+#pragma unroll 1
+        for (uint32_t i = max((uint32_t)S, full_rounds * S); i < n_it + S; i++) {
+            const uint32_t s = i % S, par_d = (i / S - 1u) & 1u;
+            if (i < n_it)
+                step(yes, yes, i, s, par_d);
+            else
+                step(yes, no, i, s, par_d);
         }
     }
 
