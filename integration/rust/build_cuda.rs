@@ -8,11 +8,14 @@ fn build_cuda() {
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "nvcc".into());
     let lib = out.join("libyume_pdq_cuda.a");
     let mut objs = vec![];
-    for f in ["api.cu", "hasher.cu", "matcher.cu", "synth.cu"] {
+    // every translation unit of yume_pdq_b200/csrc (kept in step with SOURCES in yume_pdq_b200/build.py;
+    // integration/rust/check.sh fails when the two lists differ)
+    for f in ["api.cu", "hasher.cu", "matcher.cu", "matcher_tc.cu", "matcher_tc4.cu", "matcher_tc4x2.cu", "matcher_tc1.cu",
+              "synth.cu", "peak.cu"] {
         let obj = out.join(f).with_extension("o");
         let ok = Command::new(&nvcc)
             .args(["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-                   "-Xcompiler", "-fPIC", "-c"])
+                   "-Xcompiler", "-fPIC", "-I", "cuda/include", "-c"])
             .arg(src.join(f)).arg("-o").arg(&obj)
             .status().expect("nvcc not found").success();
         assert!(ok, "nvcc failed on {f}");

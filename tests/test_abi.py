@@ -91,3 +91,13 @@ def test_header_is_valid_c_and_example_links(tmp_path):
     if yp.device_count() == 0:      # no CPU fallback: the example reports the missing device and exits 2
         r = subprocess.run([str(exe)], capture_output=True, timeout=120)
         assert r.returncode == 2 and b"no CPU fallback" in r.stderr
+
+
+def test_rust_overlay_lists_every_cuda_source():
+    """integration/rust/check.sh: build_cuda.rs must compile every translation unit that
+    yume_pdq_b200/build.py compiles; without cargo the script stops there and says SKIPPED."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["bash", os.path.join(root, "integration", "rust", "check.sh")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "CUDA sources" in r.stdout
