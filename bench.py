@@ -57,9 +57,9 @@ N_PLANT = 64
 # DRAM bytes (read + written) per database row / per frame that ONE launch of each kernel moved under `ncu --set full`
 # at the default sizes (tools/ncu_full.sh -> profiles/r02q/traffic.csv); None = not captured for this build
 TRAFFIC_SOURCE = "profiles/r02q/traffic.csv (ncu --set full of this build's kernels, one GPU, default sizes)"
-TRAFFIC_TENSOR_PER_ROW = None
-TRAFFIC_HASH_PER_FRAME = None
-TRAFFIC_SCAN_PER_ROW = None
+TRAFFIC_TENSOR_PER_ROW = 17.139       # match_tensor4x2_kernel<X2Large>, 32768 needles: 164.0 MB read + 7.4 MB written / 10,000,384 rows
+TRAFFIC_HASH_PER_FRAME = 1048602.9    # hash_fused_kernel: 1236.2 MB read + 5.4 MB written / 1184 frames (algorithmic 1,048,896)
+TRAFFIC_SCAN_PER_ROW = 17.249         # match_rows_m_kernel<N = 8>: 160.0 MB read + 12.5 MB written / 10,000,384 rows (algorithmic 16)
 
 
 def env_int(name, default):

@@ -194,3 +194,37 @@ def test_full_size_batch_properties(cuda, kernel, oracle):
     assert (hashes[idx] == want_h).all()
     assert np.array_equal(a["pdqf"].cpu().numpy()[idx], want_p)
     assert np.array_equal(a["quality"].cpu().numpy()[idx], want_q)
+
+
+def test_tent_residue_weights_documented_deviation(kernel, oracle):
+    """The reference's 7x7 tent LUT has two ~1e-40 residues in its border (TENT[0][4], TENT[0][5]: an artefact of the
+    128-bit impulse-response procedure, build.rs:334-381); the GPU kernel reads 5x5 windows and does not apply them
+    ('no test constructs the one input where it matters').  This is that input: one output whose 5x5
+    window is exactly zero while the two border pixels the residues touch are not.
+      * 8-bit-range pixels (255): the oracle's output there is 255 x 1e-40 ~ 3e-38 where the GPU writes 0 -- the ONLY
+        element of the 127 x 127 tent image that differs -- and PDQF, hashes, quality, thresholds are bit-identical;
+      * absurd pixels (3e37): the oracle's output there is ~3e-3, the GPU's still 0; everything else is identical and
+        the hashes still agree because the neighbouring outputs (~1e36) dominate every DCT coefficient."""
+    import json
+    import os
+    luts = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "yume_pdq_luts.h")).read()
+    import re
+    m = re.search(r"YUME_PDQ_TENT_WEIGHT_BITS\[7 \* 7\] = \{(.*?)\};", luts, re.S)
+    w = np.array([int(x, 16) for x in re.findall(r"0x[0-9a-fA-F]+", m.group(1))], dtype=np.uint32).view(np.float32).reshape(7, 7)
+    assert 0 < w[0, 4] < 2e-40 and 0 < w[0, 5] < 2e-40
+    oi, oj = 60, 70                                   # output (oi, oj): window centre (4 (oi + 1), 4 (oj + 1))
+    cy, cx = 4 * (oi + 1), 4 * (oj + 1)
+    for pixel in (255.0, 3e37):
+        frame = np.zeros((512, 512), dtype=np.float32)
+        frame[cy - 3, cx + 1] = pixel                  # under TENT[0][4]
+        frame[cy - 3, cx + 2] = pixel                  # under TENT[0][5]
+        want = oracle.jarosz_compress(frame)
+        got = kernel.jarosz_compress(frame[None])[0]
+        assert want[oi, oj] > 0 and want[oi, oj] == np.float32(np.float32(w[0, 4] * np.float32(pixel)) + np.float32(w[0, 5] * np.float32(pixel)))
+        assert got[oi, oj] == 0.0
+        diff = np.argwhere(got.view(np.uint32) != want.view(np.uint32))
+        assert diff.tolist() == [[oi, oj]]             # the single element the residues reach alone
+        g = kernel.hash_batch(frame[None], want_pdqf=True)
+        wh, wq, wt, wp = oracle.hash_all_dihedrals(frame[None])
+        assert np.array_equal(g["hashes"], wh) and np.array_equal(g["quality"], wq)
+        assert np.array_equal(g["pdqf"].view(np.uint32), wp.view(np.uint32)) and np.array_equal(g["thresholds"], wt)
