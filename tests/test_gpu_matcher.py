@@ -487,3 +487,45 @@ def test_auto_keeps_the_filter_on_near_duplicate_families(cuda, oracle):
     for algo in (cuda.ALGO_TENSOR_PAIRED, cuda.ALGO_TENSOR_FULL):        # candidate-list overflow -> inline verification
         assert np.array_equal(_find_device_np(cuda, m, nd, q, algo, 1 << 20), want)
     db.close()
+
+
+@pytest.mark.parametrize("q", [1, 8, 9, 16, 17, 32])
+@pytest.mark.parametrize("n_rows", [1, 127, 128, 129, 256, 257, 148 * 256 * 3 + 5, 300_001])
+def test_rows_in_m_tensor_scan(cuda, oracle, q, n_rows):
+    """ALGO_TENSOR_ROWS (matcher_tc1.cu): 128-row tiles, T per work unit, units dealt round-robin to (CTA, worker group);
+    plants sit on tile and unit edges, in the last (partial) unit, in every TMEM lane quadrant and against every needle
+    slot of the three instantiations (N = 8, 16, 32); needles with no / all prefix bits set move the bias constant to
+    its extremes (threshold - popc122 = 31 .. -91); an all-zero tail row (the padding of a partial tile) must not match
+    a needle with fewer than `threshold` set prefix bits."""
+    rng = np.random.default_rng(n_rows * 7 + q)
+    rows = oracle.synth_db(n_rows, first_row=3)
+    needles = rng.integers(0, 256, size=(q, 32), dtype=np.uint8)
+    needles[0, :16] = 0                                   # popc(prefix) = 0: bias + 31
+    if q > 1:
+        needles[q - 1, :16] = 0xFF                        # popc(prefix) = 128: bias - 91
+    if q > 2:
+        needles[1, :16] = np.packbits(np.arange(128) % 5 == 0)     # few set bits, some under the six constant positions
+    edges = [r for r in (0, 31, 32, 63, 64, 95, 96, 127, 128, 255, 256, 511, 512, 148 * 128 - 1, 148 * 128, 148 * 256 - 1,
+                         148 * 256, 3 * 148 * 256 - 1, 3 * 148 * 256, n_rows - 2, n_rows - 1) if 0 <= r < n_rows]
+    for k, r in enumerate(edges):
+        lo = int(rng.integers(0, 20))
+        rows[r] = _flip_in(needles[k % q], lo, int(rng.integers(0, 33 - lo)), rng)     # 0 .. 32 bits away
+    if n_rows > 1000:
+        for k, r in enumerate(rng.choice(n_rows, size=300, replace=False)):
+            rows[r] = _flip_in(needles[k % q], int(rng.integers(0, 34)), int(rng.integers(0, 8)), rng)
+        # differences confined to the six hash bits the filter does not see (bits 0, 4 of bytes 0..2): candidates, and
+        # matches or not by the full distance alone
+        for k, r in enumerate(rng.choice(n_rows, size=24, replace=False)):
+            row = _flip_in(needles[k % q], 29, 0, rng)
+            row[:3] ^= np.uint8(0x11)
+            rows[r] = row
+    want = sorted(match_tuples(oracle.matcher_find(rows, needles, 31)))
+    db = cuda.CudaVectorDatabase(rows, global_row_offset=10**10)
+    m = cuda.CudaMatcher(db, 31)
+    want = [(r + 10**10, n, d) for r, n, d in want]
+    assert _find_device(cuda, m, needles, cuda.ALGO_TENSOR_ROWS) == want
+    assert _find_device(cuda, m, needles, cuda.ALGO_AUTO) == want
+    for thr in (0, 30, 40) + ((128,) if n_rows < 1000 else ()):       # 128: half of all pairs match
+        w = sorted((r + 10**10, n, d) for r, n, d in match_tuples(oracle.matcher_find(rows, needles, thr)))
+        assert _find_device(cuda, cuda.CudaMatcher(db, thr), needles, cuda.ALGO_TENSOR_ROWS, cap=1 << 18) == w, thr
+    db.close()
