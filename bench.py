@@ -489,10 +489,11 @@ def main():
     scan_bytes = shard_rows * 32
     share = m_mean / (m_mean + h_mean)
     # (3c) N > 1: the sharded 8-needle query end to end (needles on rank 0 -> broadcast -> N shard scans -> OR)
-    sharded_e2e = None
+    sharded_e2e = sharded_p2p = sharded_p2p_root = p2p_stamps = None
     if n_gpus > 1:
         q8 = n8.clone()
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        flush_small = flush
 
         def sharded_scan():
             dist.broadcast(q8, src=0)
@@ -511,6 +512,26 @@ def main():
             sharded_scan()
             ts.append((time.perf_counter() - t0) * 1e6)
         sharded_e2e = max_over_ranks(float(np.median(ts)))
+
+        # the same query over peer memory (yume_pdq_cuda_mailbox_*: CUDA IPC mailboxes, plain NVLink stores ordered by
+        # flags, no collective): the needles start in HOST memory on rank 0, the answer ends as a host bit mask on rank 0
+        host_q8 = n8.cpu().numpy()
+        p2p_mask = None
+        for _ in range(5):
+            p2p_mask = sm.scan_from(host_q8 if rank == 0 else None, 8, root=0)
+        barrier()
+        ts = []
+        for _ in range(30):
+            flush_small.sum()     # evict the shard's prefix plane from L2 as the flushed kernel timings do
+            torch.cuda.synchronize()
+            if n_gpus > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            p2p_mask = sm.scan_from(host_q8 if rank == 0 else None, 8, root=0)
+            ts.append((time.perf_counter() - t0) * 1e6)
+        sharded_p2p = max_over_ranks(float(np.median(ts)))
+        sharded_p2p_root = float(np.median(ts)) if rank == 0 else None
+        p2p_stamps = sm._mailbox.last_timing() if rank == 0 else None
     worst = None
     if rank == 0 and not args.no_worst_case:
         worst = worst_case_leg(args, yp, torch, dev, local_rank, shard_rows, flush)
@@ -584,6 +605,13 @@ def main():
             "rows_per_s": shard_rows / (s_mean * 1e-3), "traffic": traffic_scan,
             "traffic_source": TRAFFIC_SOURCE,
             "needle_batches_us": batch_us,
+            "sharded_p2p_us": sharded_p2p, "sharded_p2p_us_on_root": sharded_p2p_root,
+            "sharded_p2p_host_stamps_us": p2p_stamps,
+            "sharded_p2p_path": None if n_gpus == 1 else
+            "8 needles in HOST memory on rank 0 -> post kernel writes them into every rank's mailbox over NVLink (CUDA IPC) -> "
+            "every rank: wait kernel, scan of its shard (L2 evicted before every query), publish kernel writes the count "
+            "into rank 0's mailbox -> rank 0: collect kernel -> host bit mask of the matching shards; no NCCL call "
+            "(ShardedMatcher.scan_from; median wall clock of 30 queries, max over ranks / on the root)",
             "sharded_e2e_us": sharded_e2e,
             "sharded_e2e_path": None if n_gpus == 1 else
             "8 needles on rank 0 -> NCCL broadcast -> every rank scans its shard -> NCCL all-reduce(MAX) of the flag -> "

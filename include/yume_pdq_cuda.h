@@ -46,6 +46,7 @@ extern "C" {
 #define YUME_PDQ_CUDA_E_CAPACITY (-3)  /* more matches than `cap`; *n_found holds the total (a lower bound once the
                                         * 32-bit device counter saturates at 0xF0000000 matches) */
 #define YUME_PDQ_CUDA_E_NOMEM (-4)
+#define YUME_PDQ_CUDA_E_TIMEOUT (-5)   /* a peer did not answer a mailbox query within 2 s */
 
 const char *yume_pdq_cuda_error_string(int code);
 int yume_pdq_cuda_device_count(void);
@@ -170,6 +171,29 @@ int yume_pdq_cuda_db_auto_state(const YumePDQ_CudaDb *db, int *fallback, uint32_
 /* overwrite rows [first, first+n) (host or device source) -- used by tests to plant */
 int yume_pdq_cuda_db_write_rows(YumePDQ_CudaDb *db, size_t first_local_row, const uint8_t *rows,
                                 size_t n);
+
+/* ---- sharded small-needle query over peer memory (one process per GPU, no collective library) -------------------
+ * The multi-GPU form of VulkanMatcher::scan (vulkan.rs:349-406): up to 32 needles on ONE rank, every rank scans its own
+ * shard, the root learns which shards matched.  Every rank owns a small mailbox in its HBM that the others map through
+ * CUDA IPC; needles and answers travel as plain stores over NVLink ordered by flags (csrc/api.cu), one stream
+ * synchronisation on the root, none of NCCL's two collectives.
+ *   create  : allocates this rank's mailbox; handle_out receives YUME_PDQ_CUDA_IPC_HANDLE_BYTES to hand to the peers
+ *   connect : handles = world x YUME_PDQ_CUDA_IPC_HANDLE_BYTES, rank-ordered (exchanged by the caller, e.g. all-gather)
+ *   scan    : COLLECTIVE -- every rank calls it once per query, in the same order, with the same q / threshold / root.
+ *             The root passes the needles (host or device pointer), the others NULL.  On the root *matched_ranks receives
+ *             a bit mask (bit r: rank r's shard holds a row within the threshold of some needle) and the call returns when
+ *             the answer is in; on the other ranks the call only enqueues on `stream` (their answer travels to the root
+ *             on the device) and *matched_ranks is 0.  YUME_PDQ_CUDA_E_TIMEOUT if a peer did not take part within 2 s. */
+#define YUME_PDQ_CUDA_IPC_HANDLE_BYTES 64
+typedef struct YumePDQ_CudaMailbox YumePDQ_CudaMailbox;
+int yume_pdq_cuda_mailbox_create(int device, int rank, int world, YumePDQ_CudaMailbox **out, uint8_t *handle_out);
+int yume_pdq_cuda_mailbox_connect(YumePDQ_CudaMailbox *mb, const uint8_t *handles);
+int yume_pdq_cuda_mailbox_destroy(YumePDQ_CudaMailbox *mb);
+int yume_pdq_cuda_mailbox_scan(YumePDQ_CudaMailbox *mb, YumePDQ_CudaDb *db, const uint8_t *needles, size_t q,
+                               uint32_t threshold, int root, uint32_t *matched_ranks, void *stream);
+/* diagnostic: host-side microsecond stamps of the last query on the root (after the post, wait, scan, publish + collect
+ * launches; answer in) */
+int yume_pdq_cuda_mailbox_last_timing(const YumePDQ_CudaMailbox *mb, double *out5);
 
 /* Kernel selection for the matcher (0 = automatic) */
 #define YUME_PDQ_CUDA_ALGO_AUTO 0

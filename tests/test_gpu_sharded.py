@@ -65,6 +65,30 @@ def _worker(rank, world, port, n_local, n_rows, result_dir):
     # the two-call path: hash, all-gather, find
     assert match_tuples(sm.find_all(hd.reshape(-1, 32))) == want
     assert sm.scan(hd.reshape(-1, 32)) is True
+    # the small-needle query over peer memory (CUDA IPC mailboxes, no collective): which shards match?
+    per = n_rows // world
+    rr = np.random.default_rng(5)
+    for trial in range(6):
+        root = trial % world
+        q = [8, 1, 32, 13, 8, 16][trial]
+        needles = rr.integers(0, 256, size=(q, 32), dtype=np.uint8)
+        if trial == 1:
+            needles[0] = flip_bits(rows[per + 7], 31, rr)            # a row of rank 1's shard, exactly at the threshold
+        if trial == 2:
+            needles[5] = flip_bits(rows[3], 10, rr)                  # both shards
+            needles[31] = flip_bits(rows[n_rows - 1], 0, rr)
+        if trial == 3:
+            needles[12] = flip_bits(rows[per - 1], 32, rr)           # one bit too far: no match
+        if trial == 4:
+            needles[:] = needles_all[:8]                             # this job's own hashes: planted rows exist somewhere
+        want_mask = 0
+        om = orc.matcher_find(rows, needles, 31)
+        for r in om["row"]:
+            want_mask |= 1 << min(int(r) // per, world - 1)
+        src = needles if trial % 2 == 0 else torch.from_numpy(needles).cuda()     # host array or device tensor
+        got_mask = sm.scan_from(src if rank == root else None, q, root=root)
+        assert got_mask == (want_mask if rank == root else 0), (trial, got_mask, want_mask)
+    assert trial == 5
     sm.close()
     np.save(os.path.join(result_dir, f"ok{rank}.npy"), np.array([len(got)]))
     dist.destroy_process_group()

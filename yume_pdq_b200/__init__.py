@@ -98,6 +98,11 @@ SIGNATURES = {
     "yume_pdq_cuda_db_len": (C.c_size_t, [_vp]),
     "yume_pdq_cuda_db_device": (C.c_int, [_vp]),
     "yume_pdq_cuda_db_planes": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "yume_pdq_cuda_mailbox_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_vp), _vp]),
+    "yume_pdq_cuda_mailbox_connect": (C.c_int, [_vp, _vp]),
+    "yume_pdq_cuda_mailbox_destroy": (C.c_int, [_vp]),
+    "yume_pdq_cuda_mailbox_last_timing": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "yume_pdq_cuda_mailbox_scan": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), _vp]),
     "yume_pdq_cuda_db_auto_state": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_uint32)]),
     "yume_pdq_cuda_db_write_rows": (C.c_int, [_vp, C.c_size_t, _vp, C.c_size_t]),
     "yume_pdq_cuda_matcher_scan": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, C.POINTER(C.c_int), _vp]),
@@ -567,6 +572,54 @@ class CudaMatcher:
                                                           self.threshold, _ptr(out_dev), cap, _ptr(count_dev),
                                                           algo, needle_base, _stream(stream or self.stream)),
                "matcher_find_device")
+
+
+IPC_HANDLE_BYTES = 64
+
+
+class PeerMailbox:
+    """This rank's end of the peer-memory query (yume_pdq_cuda_mailbox_*): `handle` goes to the peers, `connect` takes
+    everyone's handles in rank order, `scan` is the collective query.  yume_pdq_b200.sharded wires it to
+    torch.distributed."""
+
+    def __init__(self, device: int, rank: int, world: int):
+        self._h = _vp()
+        buf = (C.c_uint8 * IPC_HANDLE_BYTES)()
+        _check(lib.yume_pdq_cuda_mailbox_create(device, rank, world, C.byref(self._h), buf), "mailbox_create")
+        self.handle = bytes(buf)
+        self.rank, self.world = rank, world
+
+    def connect(self, handles):
+        blob = b"".join(handles)
+        assert len(blob) == self.world * IPC_HANDLE_BYTES
+        _check(lib.yume_pdq_cuda_mailbox_connect(self._h, C.c_char_p(blob)), "mailbox_connect")
+
+    def scan(self, db: "CudaVectorDatabase", needles, q: int, threshold: int, root: int = 0, stream=None) -> int:
+        """Bit mask of the ranks whose shard matched (on the root; 0 elsewhere)."""
+        if isinstance(needles, np.ndarray):
+            needles = np.ascontiguousarray(needles, dtype=np.uint8).reshape(-1, 32)
+        m = C.c_uint32(0)
+        _check(lib.yume_pdq_cuda_mailbox_scan(self._h, db._h, _ptr(needles), q, threshold, root, C.byref(m), _stream(stream)),
+               "mailbox_scan")
+        return int(m.value)
+
+    def last_timing(self):
+        """Host-side microsecond stamps of the last query on the root: after the post / wait / scan / publish + collect
+        launches, and when the answer arrived."""
+        t = (C.c_double * 5)()
+        _check(lib.yume_pdq_cuda_mailbox_last_timing(self._h, t), "mailbox_last_timing")
+        return list(t)
+
+    def close(self):
+        if self._h:
+            lib.yume_pdq_cuda_mailbox_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def synth_frames(frames_dev, n: int, first_frame: int = 0, seed: int = 0x79756D652D706471, kind: int = 1,

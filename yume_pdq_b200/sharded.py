@@ -105,6 +105,7 @@ class ShardedMatcher:
         self.begin, self.end = shard_range(n_rows, self.rank, self.world)
         self.db = rows_factory(self.begin, self.end, device)
         self.matcher = CudaMatcher(self.db, threshold)
+        self._mailbox = None
 
     def find_all(self, local_needles, cap: int = 1 << 16) -> np.ndarray:
         """local_needles: this rank's [q_local, 32] uint8 CUDA tensor.  Returns the merged global match
@@ -203,5 +204,27 @@ class ShardedMatcher:
         dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)   # host-side OR of the flags
         return bool(flag.item())
 
+    def scan_from(self, needles, q: int, root: int = 0) -> int:
+        """The sharded small-needle query over peer memory (no collective): up to 32 needles held by `root` (host array
+        or device tensor; the other ranks pass None), every rank scans its shard.  COLLECTIVE: every rank calls it.
+        Returns, on the root, the bit mask of the ranks whose shard holds a match (0 elsewhere) -- the multi-GPU form of
+        VulkanMatcher::scan (vulkan.rs:349-406).  The mailboxes are set up on first use (one all-gather of 64-byte
+        CUDA IPC handles)."""
+        if self.world == 1:
+            return int(self.matcher.scan(needles))
+        if self._mailbox is None:
+            import torch.distributed as dist
+            from . import PeerMailbox
+            mb = PeerMailbox(self.device, self.rank, self.world)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, mb.handle, group=self.group)
+            mb.connect(handles)
+            dist.barrier(group=self.group)
+            self._mailbox = mb
+        return self._mailbox.scan(self.db, needles if self.rank == root else None, q, self.matcher.threshold, root)
+
     def close(self):
+        if self._mailbox is not None:
+            self._mailbox.close()
+            self._mailbox = None
         self.db.close()
