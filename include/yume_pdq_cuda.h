@@ -205,7 +205,7 @@ int yume_pdq_cuda_mailbox_last_timing(const YumePDQ_CudaMailbox *mb, double *out
 #define YUME_PDQ_CUDA_ALGO_TENSOR_FULL 6    /* kind::mxf4, always the full 256-bit dot product (threshold <= 127) */
 #define YUME_PDQ_CUDA_ALGO_TENSOR_PREFIX 7  /* kind::mxf4, always the 128-bit prefix filter (threshold <= 63) */
 #define YUME_PDQ_CUDA_ALGO_TENSOR_PAIRED 8  /* kind::mxf4, 128-bit prefix filter with two rows per f32 accumulator (s16x2 fields; threshold <= 60) */
-#define YUME_PDQ_CUDA_ALGO_TENSOR_ROWS 9    /* kind::mxf4 with the database rows in the M dimension (operand A in tensor memory): 1 .. 32 needles, 128-bit prefix filter + exact check */
+#define YUME_PDQ_CUDA_ALGO_TENSOR_ROWS 9    /* kind::mxf4 with the database rows in the M dimension (operand A in tensor memory): 1 .. 64 needles, 122-bit prefix filter + exact check */
 
 /* PDQMatcher::scan (matching/mod.rs:72-79): *matched = 1 iff any needle is within
  * `threshold` (inclusive) of any row.  needles q x 32 bytes, host or device. */

@@ -40,7 +40,7 @@ def test_planted_vs_oracle_all_algos(cuda, oracle, n_rows, q):
     assert m.find_min(needles) == oracle.matcher_find_min(rows, needles, 31)
     for algo in (cuda.ALGO_EXACT, cuda.ALGO_TILED, cuda.ALGO_TENSOR, cuda.ALGO_TENSOR_I8,
                  cuda.ALGO_TENSOR_FULL, cuda.ALGO_TENSOR_PREFIX, cuda.ALGO_TENSOR_PAIRED) + (
-                     (cuda.ALGO_TENSOR_ROWS,) if q <= 32 else ()):
+                     (cuda.ALGO_TENSOR_ROWS,) if q <= 64 else ()):
         assert _find_device(cuda, m, needles, algo) == sorted(want), algo
     db.close()
 
@@ -489,12 +489,12 @@ def test_auto_keeps_the_filter_on_near_duplicate_families(cuda, oracle):
     db.close()
 
 
-@pytest.mark.parametrize("q", [1, 8, 9, 16, 17, 32])
+@pytest.mark.parametrize("q", [1, 8, 9, 16, 17, 32, 33, 64])
 @pytest.mark.parametrize("n_rows", [1, 127, 128, 129, 256, 257, 148 * 256 * 3 + 5, 300_001])
 def test_rows_in_m_tensor_scan(cuda, oracle, q, n_rows):
     """ALGO_TENSOR_ROWS (matcher_tc1.cu): 128-row tiles, T per work unit, units dealt round-robin to (CTA, worker group);
     plants sit on tile and unit edges, in the last (partial) unit, in every TMEM lane quadrant and against every needle
-    slot of the three instantiations (N = 8, 16, 32); needles with no / all prefix bits set move the bias constant to
+    slot of the four instantiations (N = 8, 16, 32, 64); needles with no / all prefix bits set move the bias constant to
     its extremes (threshold - popc122 = 31 .. -91); an all-zero tail row (the padding of a partial tile) must not match
     a needle with fewer than `threshold` set prefix bits."""
     rng = np.random.default_rng(n_rows * 7 + q)

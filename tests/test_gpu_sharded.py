@@ -89,6 +89,23 @@ def _worker(rank, world, port, n_local, n_rows, result_dir):
         got_mask = sm.scan_from(src if rank == root else None, q, root=root)
         assert got_mask == (want_mask if rank == root else 0), (trial, got_mask, want_mask)
     assert trial == 5
+    # many queries back to back, alternating roots: sequence numbers, mailbox reuse, no rank runs ahead of a scan
+    fixed = [rr.integers(0, 256, size=(8, 32), dtype=np.uint8) for _ in range(4)]
+    fixed[1][2] = flip_bits(rows[per + 11], 5, rr)
+    fixed[2][7] = flip_bits(rows[17], 31, rr)
+    fixed[3][0] = flip_bits(rows[per - 2], 3, rr)
+    fixed[3][1] = flip_bits(rows[n_rows - 3], 30, rr)
+    masks = []
+    for nd in fixed:
+        mk = 0
+        for r in orc.matcher_find(rows, nd, 31)["row"]:
+            mk |= 1 << min(int(r) // per, world - 1)
+        masks.append(mk)
+    assert masks == [0, 2, 1, 3]
+    for it in range(200):
+        k, root = it % 4, (it // 3) % world
+        got_mask = sm.scan_from(fixed[k] if rank == root else None, 8, root=root)
+        assert got_mask == (masks[k] if rank == root else 0), (it, got_mask)
     sm.close()
     np.save(os.path.join(result_dir, f"ok{rank}.npy"), np.array([len(got)]))
     dist.destroy_process_group()

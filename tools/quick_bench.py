@@ -112,7 +112,7 @@ def main():
         for n in (1_250_048, (10_000_000 // 2048 + 1) * 2048):
             db = yp.CudaVectorDatabase(synthetic_rows=n)
             m = yp.CudaMatcher(db, 31)
-            for q in (8, 16, 32):
+            for q in (8, 16, 32, 64):
                 needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
                 med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 16, cnt, algo=yp.ALGO_TENSOR_ROWS), iters=20, warm=3, flush=flush)
                 print(f"[{tag}] rows-in-M {n:9d} x {q:3d}: median {med:8.1f} us  best {best:8.1f} us  {n * 16 / med / 1e3:7.1f} GB/s (prefix plane)")

@@ -276,12 +276,12 @@ int launch_match(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_
     if (algo == YUME_PDQ_CUDA_ALGO_AUTO) {
         // Measured on B200 (10M rows, threshold 31; profiles/r02y, r03a quick.log): tiled POPC kernel 53 us for 8 needles,
         // 86 us for 16, 157 us for 32 (2.1e12 pairs/s from there on); rows-in-M tensor kernel 41 us up to 8 needles, 45 us
-        // up to 16, 55 us up to 32; needles-in-M (paired) tensor kernel 74..86 us for anything up to 128 needles (one
+        // up to 16, 55 us up to 32, 70 us up to 64; needles-in-M (paired) tensor kernel 74..86 us for anything up to 128 needles (one
         // launch, X2One), 142 us for 256, 230 us for 512, 0.39 ms for 1024.  Above threshold 36 the large-batch tensor path
         // is the unpaired full kernel (1024 needles 0.8 ms vs tiled 4.7 ms); the 96-bit prefix bound of the POPC kernels
         // stops filtering once the threshold approaches 48.  A persistent tensor launch costs ~10 us before the first row:
         // small shards stay on the POPC kernel (568k rows x 8: 12.3 us either way, 142k rows: 9.2 vs 10.3).
-        if (q <= 32 && threshold <= 40 && n_rows >= (q <= 8 ? 1000000u : 500000u))
+        if (q <= 64 && threshold <= 40 && n_rows >= (q <= 8 ? 1000000u : 500000u))
             algo = YUME_PDQ_CUDA_ALGO_TENSOR_ROWS;
         else if (q >= (threshold <= 36 ? 14u : 512u) && (q >= 512 || n_rows >= 100000))
             algo = YUME_PDQ_CUDA_ALGO_TENSOR;

@@ -1,4 +1,4 @@
-// matcher_tc1.cu -- tensor-core Hamming scan for SMALL needle batches (1 .. 32 needles: the 8 dihedral hashes of one
+// matcher_tc1.cu -- tensor-core Hamming scan for SMALL needle batches (1 .. 64 needles: the 8 dihedral hashes of one
 // image, the reference's headline query): DATABASE ROWS IN THE M DIMENSION, operand A written to tensor memory
 // straight from registers.
 //
@@ -94,7 +94,8 @@ struct X1Cfg {
 #endif
 // Measured on a B200, 10M rows x {8, 16, 32} needles (profiles/r02y .. r03a; T tiles per unit, G groups, S slots):
 //   N = 8:  T2 G4 S2 41.0 us, T3 G3 S2 41.1, T4 G2 S2 45.1        N = 16: T2 G3 S2 45.2, T3 G2 S2 49.2, T1 G4 S3 51.2
-//   N = 32: T1 G4 S2 55.4, T1 G3 S3 59.5, T2 G2 S2 59.3           (needles-in-M kernel: 77 us for any of them)
+//   N = 32: T1 G4 S2 55.4, T1 G3 S3 59.5, T2 G2 S2 59.3           N = 64: T1 G3 S2 69.8
+//   (needles-in-M kernel: 77 .. 80 us for any of them)
 #ifndef X1_T8_CFG
 #define X1_T8_CFG 2
 #define X1_G8_CFG 4
@@ -103,6 +104,12 @@ struct X1Cfg {
 using X1N8 = X1Cfg<8, X1_T8_CFG, X1_G8_CFG, X1_S8_CFG, X1_R_CFG>;
 using X1N16 = X1Cfg<16, X1_T16_CFG, X1_G16_CFG, X1_S16_CFG, X1_R_CFG>;
 using X1N32 = X1Cfg<32, X1_T32_CFG, X1_G32_CFG, X1_S32_CFG, X1_R_CFG>;
+#ifndef X1_G64_CFG
+#define X1_T64_CFG 1
+#define X1_G64_CFG 3
+#define X1_S64_CFG 2
+#endif
+using X1N64 = X1Cfg<64, X1_T64_CFG, X1_G64_CFG, X1_S64_CFG, X1_R_CFG>;
 
 __device__ __forceinline__ uint64_t x1_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo)
 {
@@ -361,8 +368,10 @@ match_rows_m_kernel(DbPlanes rows, uint64_t n_rows, uint32_t q, Tc4Sink sink)
                         T4_LD_X8(v[t], 0, col + 16 * T + N * t);
                     else if constexpr (N == 16)
                         T4_LD_X16(v[t], 0, col + 16 * T + N * t);
-                    else
+                    else if constexpr (N == 32)
                         T4_LD_X32(v[t], 0, col + 16 * T + N * t);
+                    else
+                        T4_LD_X64(v[t], 0, col + 16 * T + N * t);
                 }
             }
             if constexpr (produce) {
@@ -464,21 +473,23 @@ int launch_x1(DbPlanes rows, size_t n_rows, uint32_t q, const Tc4Sink &sink, int
 
 }  // namespace
 
-// 1 .. 32 needles, any threshold (the prefix filter only thins the pairs; it is useful up to ~48)
+// 1 .. 64 needles, any threshold up to 128 (the prefix filter only thins the pairs; it is useful up to ~48)
 int launch_match_tensor_rows(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles, size_t q,
                              uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
                              unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base)
 {
     if (n_rows == 0 || q == 0)
         return 0;
-    if (q > 32 || threshold > 128)
+    if (q > 64 || threshold > 128)
         return YUME_PDQ_CUDA_E_INVALID;
     Tc4Sink sink{out, cap, count, min_key, row_offset, (uint64_t)q, mode, needle_base, reinterpret_cast<const uint4 *>(needles), threshold};
     if (q <= 8)
         return launch_x1<X1N8>(rows, n_rows, (uint32_t)q, sink, sm_count, s);
     if (q <= 16)
         return launch_x1<X1N16>(rows, n_rows, (uint32_t)q, sink, sm_count, s);
-    return launch_x1<X1N32>(rows, n_rows, (uint32_t)q, sink, sm_count, s);
+    if (q <= 32)
+        return launch_x1<X1N32>(rows, n_rows, (uint32_t)q, sink, sm_count, s);
+    return launch_x1<X1N64>(rows, n_rows, (uint32_t)q, sink, sm_count, s);
 }
 
 }  // namespace ypdq
