@@ -489,7 +489,7 @@ def main():
     scan_bytes = shard_rows * 32
     share = m_mean / (m_mean + h_mean)
     # (3c) N > 1: the sharded 8-needle query end to end (needles on rank 0 -> broadcast -> N shard scans -> OR)
-    sharded_e2e = sharded_p2p = sharded_p2p_root = p2p_stamps = None
+    sharded_e2e = sharded_p2p = sharded_p2p_root = p2p_stamps = p2p_forms = None
     if n_gpus > 1:
         q8 = n8.clone()
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -517,20 +517,28 @@ def main():
         # flags, no collective): the needles start in HOST memory on rank 0, the answer ends as a host bit mask on rank 0
         host_q8 = n8.cpu().numpy()
         p2p_mask = None
-        for _ in range(5):
-            p2p_mask = sm.scan_from(host_q8 if rank == 0 else None, 8, root=0)
-        barrier()
-        ts = []
-        for _ in range(30):
-            flush_small.sum()     # evict the shard's prefix plane from L2 as the flushed kernel timings do
-            torch.cuda.synchronize()
-            if n_gpus > 1:
-                dist.barrier()
-            t0 = time.perf_counter()
-            p2p_mask = sm.scan_from(host_q8 if rank == 0 else None, 8, root=0)
-            ts.append((time.perf_counter() - t0) * 1e6)
-        sharded_p2p = max_over_ranks(float(np.median(ts)))
-        sharded_p2p_root = float(np.median(ts)) if rank == 0 else None
+        p2p_forms = {}
+        # FUSED: post, wait, rows-in-M scan, publish and collect inside ONE launch per rank (matcher_tc1.cu);
+        # SEPARATE: five launches on the root, three elsewhere, around ALGO_AUTO's kernel; AUTO (the default, reported
+        # as sharded_p2p_us): fused where ALGO_AUTO's kernel for the shard is the rows-in-M scan (>= 1M rows)
+        for form, mode in (("fused", yp.MAILBOX_FUSED), ("separate", yp.MAILBOX_SEPARATE), ("auto", yp.MAILBOX_AUTO)):
+            for i in range(5):
+                p2p_mask = sm.scan_from(host_q8 if rank == 0 else None, 8, root=0)
+                if i == 0:
+                    sm._mailbox.set_mode(mode)
+            barrier()
+            ts = []
+            for _ in range(30):
+                flush_small.sum()     # evict the shard's prefix plane from L2 as the flushed kernel timings do
+                torch.cuda.synchronize()
+                if n_gpus > 1:
+                    dist.barrier()
+                t0 = time.perf_counter()
+                p2p_mask = sm.scan_from(host_q8 if rank == 0 else None, 8, root=0)
+                ts.append((time.perf_counter() - t0) * 1e6)
+            p2p_forms[form] = {"us": max_over_ranks(float(np.median(ts))), "us_on_root": float(np.median(ts))}
+        sharded_p2p = p2p_forms["auto"]["us"]
+        sharded_p2p_root = p2p_forms["auto"]["us_on_root"] if rank == 0 else None
         p2p_stamps = sm._mailbox.last_timing() if rank == 0 else None
     worst = None
     if rank == 0 and not args.no_worst_case:
@@ -607,10 +615,13 @@ def main():
             "needle_batches_us": batch_us,
             "sharded_p2p_us": sharded_p2p, "sharded_p2p_us_on_root": sharded_p2p_root,
             "sharded_p2p_host_stamps_us": p2p_stamps,
+            "sharded_p2p_forms": None if n_gpus == 1 else p2p_forms,
+            "sharded_p2p_form": None if n_gpus == 1 else ("fused" if rows_in_m else "separate"),
             "sharded_p2p_path": None if n_gpus == 1 else
-            "8 needles in HOST memory on rank 0 -> post kernel writes them into every rank's mailbox over NVLink (CUDA IPC) -> "
-            "every rank: wait kernel, scan of its shard (L2 evicted before every query), publish kernel writes the count "
-            "into rank 0's mailbox -> rank 0: collect kernel -> host bit mask of the matching shards; no NCCL call "
+            "8 needles in HOST memory on rank 0 -> written into every rank's mailbox over NVLink (CUDA IPC) -> every rank "
+            "waits for its mailbox's flag, scans its shard (L2 evicted before every query), writes its count into rank 0's "
+            "mailbox -> rank 0 collects -> host bit mask of the matching shards; no NCCL call.  fused: all of it inside one "
+            "launch of the rows-in-M scan per rank; separate: post / wait / scan / publish / collect kernels "
             "(ShardedMatcher.scan_from; median wall clock of 30 queries, max over ranks / on the root)",
             "sharded_e2e_us": sharded_e2e,
             "sharded_e2e_path": None if n_gpus == 1 else

@@ -191,6 +191,15 @@ int yume_pdq_cuda_mailbox_connect(YumePDQ_CudaMailbox *mb, const uint8_t *handle
 int yume_pdq_cuda_mailbox_destroy(YumePDQ_CudaMailbox *mb);
 int yume_pdq_cuda_mailbox_scan(YumePDQ_CudaMailbox *mb, YumePDQ_CudaDb *db, const uint8_t *needles, size_t q,
                                uint32_t threshold, int root, uint32_t *matched_ranks, void *stream);
+/* How a rank runs its part of a query.  AUTO: one launch that carries the whole exchange (needles out, wait, shard scan,
+ * answer back, collection on the root) wherever the shard scan is the rows-in-M tensor kernel -- the kernel ALGO_AUTO
+ * picks for shards of >= 1M rows at thresholds <= 40 -- and separate post / wait / scan / publish / collect launches
+ * around ALGO_AUTO's kernel elsewhere.  SEPARATE / FUSED force one form (FUSED: any shard size, threshold <= 128).  The
+ * two forms speak the same flag protocol: ranks may differ. */
+#define YUME_PDQ_CUDA_MAILBOX_AUTO 0
+#define YUME_PDQ_CUDA_MAILBOX_SEPARATE 1
+#define YUME_PDQ_CUDA_MAILBOX_FUSED 2
+int yume_pdq_cuda_mailbox_set_mode(YumePDQ_CudaMailbox *mb, int mode);
 /* diagnostic: host-side microsecond stamps of the last query on the root (after the post, wait, scan, publish + collect
  * launches; answer in) */
 int yume_pdq_cuda_mailbox_last_timing(const YumePDQ_CudaMailbox *mb, double *out5);

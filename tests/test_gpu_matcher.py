@@ -529,3 +529,45 @@ def test_rows_in_m_tensor_scan(cuda, oracle, q, n_rows):
         w = sorted((r + 10**10, n, d) for r, n, d in match_tuples(oracle.matcher_find(rows, needles, thr)))
         assert _find_device(cuda, cuda.CudaMatcher(db, thr), needles, cuda.ALGO_TENSOR_ROWS, cap=1 << 18) == w, thr
     db.close()
+
+
+@pytest.mark.parametrize("q", [1, 8, 13, 32])
+@pytest.mark.parametrize("n_rows", [1, 129, 148 * 256 + 77, 1_200_003])
+def test_mailbox_query_one_rank(cuda, oracle, q, n_rows):
+    """The peer-memory query with a world of ONE rank (this GPU is root and only peer): the fused form -- post, wait,
+    rows-in-M scan, publish and collect inside one launch (matcher_tc1.cu, MailboxHook) -- and the separate-launch form
+    must both answer what the oracle says, for host and device needles, query after query on the same mailbox (the
+    two match counters alternate; the finished-CTA counter is reset by the last CTA)."""
+    import torch
+    rng = np.random.default_rng(n_rows + q)
+    rows = oracle.synth_db(n_rows, first_row=11)
+    db = cuda.CudaVectorDatabase(rows)
+    mb = cuda.PeerMailbox(0, 0, 1)
+    mb.connect([mb.handle])
+    queries = []
+    for k in range(6):
+        needles = rng.integers(0, 256, size=(q, 32), dtype=np.uint8)
+        r = int(rng.integers(0, n_rows))
+        if k == 1:
+            needles[q - 1] = flip_bits(rows[r], 31, rng)          # exactly at the threshold, last needle slot
+        if k == 2:
+            needles[0] = flip_bits(rows[r], 32, rng)              # one bit too far
+        if k == 3:
+            needles[q // 2] = flip_bits(rows[n_rows - 1], 0, rng)     # last row (partial tile)
+        if k == 5:
+            needles[0] = flip_bits(rows[0], 7, rng)
+        queries.append((needles, int(len(oracle.matcher_find(rows, needles, 31)["row"]) > 0)))
+    assert queries[1][1] == 1 and queries[3][1] == 1 and queries[0][1] == 0
+    for mode in (cuda.MAILBOX_AUTO, cuda.MAILBOX_FUSED, cuda.MAILBOX_SEPARATE, cuda.MAILBOX_FUSED):
+        mb.set_mode(mode)
+        for k, (needles, want) in enumerate(queries):
+            src = needles if k % 2 == 0 else torch.from_numpy(needles).cuda()
+            assert mb.scan(db, src, q, 31, root=0) == want, (mode, k)
+    # other thresholds through the fused form (the filter is exact at every threshold; 128 matches half of all pairs)
+    mb.set_mode(cuda.MAILBOX_FUSED)
+    for thr in (0, 40, 128):
+        for needles, _ in queries[:4]:
+            want = int(len(oracle.matcher_find(rows, needles, thr)["row"]) > 0)
+            assert mb.scan(db, needles, q, thr, root=0) == want, thr
+    mb.close()
+    db.close()

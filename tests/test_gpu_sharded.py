@@ -120,3 +120,84 @@ def test_two_gpu_sharded_screen(tmp_path, oracle):
     mp.spawn(_worker, args=(world, _free_port(), 150, 60_001, str(tmp_path)), nprocs=world, join=True)
     counts = [int(np.load(tmp_path / f"ok{r}.npy")[0]) for r in range(world)]
     assert counts[0] == counts[1] > 60
+
+
+def _fused_worker(rank, world, port, n_rows, result_dir):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (here, os.path.dirname(here)):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+
+    import yume_pdq_b200 as yp
+    from oracle import pyoracle
+    from yume_pdq_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    orc = pyoracle.get()
+    rows = orc.synth_db(n_rows, first_row=3)
+    per = n_rows // world
+
+    def factory(begin, end, device):
+        return yp.CudaVectorDatabase(rows[begin:end], device=device, global_row_offset=begin)
+
+    sm = sharded.ShardedMatcher(n_rows, 31, factory, device=rank)
+    rr = np.random.default_rng(23)
+    queries = []
+    for k in range(8):
+        q = [8, 1, 32, 13, 8, 16, 8, 8][k]
+        needles = rr.integers(0, 256, size=(q, 32), dtype=np.uint8)
+        if k == 1:
+            needles[0] = flip_bits(rows[per + 7], 31, rr)            # rank 1's shard, exactly at the threshold
+        if k == 2:
+            needles[5] = flip_bits(rows[3], 10, rr)                  # both shards
+            needles[31] = flip_bits(rows[n_rows - 1], 0, rr)
+        if k == 3:
+            needles[12] = flip_bits(rows[per - 1], 32, rr)           # one bit too far: no match
+        if k == 4:
+            needles[7] = flip_bits(rows[per - 1], 30, rr)            # last row of rank 0's shard
+        if k == 6:
+            needles[0] = flip_bits(rows[per], 1, rr)                 # first row of rank 1's shard
+        mk = 0
+        for r in orc.matcher_find(rows, needles, 31)["row"]:
+            mk |= 1 << min(int(r) // per, world - 1)
+        queries.append((q, needles, mk))
+    assert [m for _, _, m in queries] == [0, 2, 3, 0, 1, 0, 2, 0]
+    assert sm.scan_from(queries[0][1] if rank == 0 else None, 8, root=0) == 0        # sets the mailboxes up
+    # shards of >= 1M rows: AUTO is the fused form (one launch per rank); then both forced forms, then MIXED forms --
+    # rank 0 fused, rank 1 separate launches and the other way round: one flag protocol
+    for mode_of in (lambda r: yp.MAILBOX_AUTO, lambda r: yp.MAILBOX_FUSED, lambda r: yp.MAILBOX_SEPARATE,
+                    lambda r: yp.MAILBOX_FUSED if r == 0 else yp.MAILBOX_SEPARATE,
+                    lambda r: yp.MAILBOX_SEPARATE if r == 0 else yp.MAILBOX_FUSED):
+        sm._mailbox.set_mode(mode_of(rank))
+        for k, (q, needles, mk) in enumerate(queries):
+            root = k % world
+            src = needles if k % 3 else torch.from_numpy(needles).cuda()
+            got = sm.scan_from(src if rank == root else None, q, root=root)
+            assert got == (mk if rank == root else 0), (k, got, mk)
+    # back to back, alternating roots and forms
+    for it in range(300):
+        k, root = it % 8, (it // 3) % world
+        sm._mailbox.set_mode(yp.MAILBOX_FUSED if (it // 5 + rank) % 3 else yp.MAILBOX_SEPARATE)
+        q, needles, mk = queries[k]
+        got = sm.scan_from(needles if rank == root else None, q, root=root)
+        assert got == (mk if rank == root else 0), (it, got, mk)
+    torch.cuda.synchronize()
+    sm.close()
+    np.save(os.path.join(result_dir, f"fused_ok{rank}.npy"), np.array([1]))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_fused_mailbox_query(tmp_path, oracle):
+    """The one-launch-per-rank form of the peer-memory query (rows-in-M scan + MailboxHook) on two 1.1M-row shards."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    world = 2
+    mp.spawn(_fused_worker, args=(world, _free_port(), 2_200_006, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"fused_ok{r}.npy") for r in range(world))

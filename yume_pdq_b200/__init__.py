@@ -30,6 +30,7 @@ MATCH_DTYPE = np.dtype([("row", "<u8"), ("needle", "<u4"), ("dist", "<u4")])
 
 ALGO_AUTO, ALGO_EXACT, ALGO_TILED, ALGO_TENSOR, ALGO_TENSOR_I8 = 0, 1, 2, 4, 5
 ALGO_TENSOR_FULL, ALGO_TENSOR_PREFIX, ALGO_TENSOR_PAIRED, ALGO_TENSOR_ROWS = 6, 7, 8, 9
+MAILBOX_AUTO, MAILBOX_SEPARATE, MAILBOX_FUSED = 0, 1, 2
 
 OP_T = 0
 OP_NEGATE_ALT_COLS_FALSE = 1
@@ -102,6 +103,7 @@ SIGNATURES = {
     "yume_pdq_cuda_mailbox_connect": (C.c_int, [_vp, _vp]),
     "yume_pdq_cuda_mailbox_destroy": (C.c_int, [_vp]),
     "yume_pdq_cuda_mailbox_last_timing": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "yume_pdq_cuda_mailbox_set_mode": (C.c_int, [_vp, C.c_int]),
     "yume_pdq_cuda_mailbox_scan": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), _vp]),
     "yume_pdq_cuda_db_auto_state": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_uint32)]),
     "yume_pdq_cuda_db_write_rows": (C.c_int, [_vp, C.c_size_t, _vp, C.c_size_t]),
@@ -602,6 +604,10 @@ class PeerMailbox:
         _check(lib.yume_pdq_cuda_mailbox_scan(self._h, db._h, _ptr(needles), q, threshold, root, C.byref(m), _stream(stream)),
                "mailbox_scan")
         return int(m.value)
+
+    def set_mode(self, mode: int):
+        """MAILBOX_AUTO / MAILBOX_SEPARATE / MAILBOX_FUSED (yume_pdq_cuda.h)."""
+        _check(lib.yume_pdq_cuda_mailbox_set_mode(self._h, mode), "mailbox_set_mode")
 
     def last_timing(self):
         """Host-side microsecond stamps of the last query on the root: after the post / wait / scan / publish + collect

@@ -1197,45 +1197,11 @@ int yume_pdq_cuda_synth_rows(int device, uint8_t *rows_dev, size_t n_rows, uint6
 //          publish kernel count -> root's result[rank], fence, root's seq_out[rank] = seq
 //   root:  collect kernel spin until every seq_out == seq, OR the counts into mapped host memory; ONE stream sync.
 // The root returns only after it has every rank's answer, so a mailbox is never overwritten while a scan still reads it.
+// Where the shard scan is the rows-in-M tensor kernel (matcher_tc1.cu) all five steps ride inside that ONE launch per
+// rank (MailboxHook): CTA 0 of the root posts, every CTA waits on its own rank's mailbox, the last CTA to finish
+// publishes and, on the root, collects.  Both forms speak the same flag protocol, so ranks may mix them.
 namespace ypdq {
 namespace {
-
-constexpr int kMailboxMaxWorld = 16;
-constexpr int kMailboxMaxNeedles = 32;
-constexpr unsigned long long kMailboxTimeoutNs = 2000000000ull;    // a peer that never posts must not hang the GPU
-
-struct MailboxMem {
-    uint4 needles[2 * kMailboxMaxNeedles];    // q x 32 B
-    unsigned int seq_in;                      // written by the root after the needles
-    unsigned int count;                       // match counter of the local scan
-    unsigned int error;                       // a wait timed out
-    unsigned int pad;
-    unsigned int seq_out[kMailboxMaxWorld];   // on the root: written by rank r after result[r]
-    unsigned int result[kMailboxMaxWorld];
-};
-struct MailboxNeedles {
-    uint4 v[2 * kMailboxMaxNeedles];          // 1 KB, by value in the launch parameters: no upload
-};
-struct MailboxPeers {
-    MailboxMem *p[kMailboxMaxWorld];
-};
-
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p)
-{
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v)
-{
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long global_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 
 __global__ void __launch_bounds__(64)
 mailbox_post_kernel(MailboxNeedles needles, const uint4 *__restrict__ needles_dev, uint32_t n_vec, MailboxPeers peers, int world,
@@ -1261,12 +1227,13 @@ __global__ void mailbox_wait_kernel(MailboxMem *mine, uint32_t seq)
             break;
         }
     }
-    mine->count = 0;
+    mine->count[seq & 1u] = 0;
 }
 
-__global__ void mailbox_publish_kernel(const MailboxMem *mine, MailboxMem *root, int rank, uint32_t seq)
+__global__ void mailbox_publish_kernel(MailboxMem *mine, MailboxMem *root, int rank, uint32_t seq)
 {
-    root->result[rank] = mine->count | (mine->error ? 0x80000000u : 0u);
+    root->result[rank] = mine->count[seq & 1u] | (mine->error ? 0x80000000u : 0u);
+    mine->count[(seq + 1u) & 1u] = 0;      // the next query's counter (a fused scan does not run a wait kernel)
     __threadfence_system();
     st_release_sys(&root->seq_out[rank], seq);
 }
@@ -1274,25 +1241,7 @@ __global__ void mailbox_publish_kernel(const MailboxMem *mine, MailboxMem *root,
 __global__ void __launch_bounds__(32)
 mailbox_collect_kernel(MailboxMem *mine, int world, uint32_t seq, volatile unsigned int *host_out)
 {
-    unsigned int r = 0, err = 0;
-    if ((int)threadIdx.x < world) {
-        const unsigned long long t0 = global_ns();
-        while (ld_acquire_sys(&mine->seq_out[threadIdx.x]) != seq) {
-            if (global_ns() - t0 > kMailboxTimeoutNs) {
-                err = 1;
-                break;
-            }
-        }
-        r = mine->result[threadIdx.x];
-    }
-    const unsigned int any = __ballot_sync(0xFFFFFFFFu, (r & 0x7FFFFFFFu) != 0);
-    const unsigned int bad = __ballot_sync(0xFFFFFFFFu, err || (r & 0x80000000u));
-    if (threadIdx.x == 0) {
-        host_out[1] = any;       // bit r: rank r's shard holds a match
-        host_out[2] = bad;
-        __threadfence_system();
-        host_out[0] = seq;
-    }
+    mailbox_collect(mine, world, seq, host_out);
 }
 
 }  // namespace
@@ -1305,6 +1254,7 @@ struct YumePDQ_CudaMailbox {
     ypdq::MailboxPeers peers{};
     unsigned int *h_out = nullptr;     // pinned, mapped: {seq, any mask, error mask}
     bool connected = false;
+    int mode = YUME_PDQ_CUDA_MAILBOX_AUTO;
     double timing_us[8] = {0};         // host-side time stamps of the last query on the root (diagnostic)
 };
 
@@ -1396,6 +1346,34 @@ int yume_pdq_cuda_mailbox_scan(YumePDQ_CudaMailbox *mb, YumePDQ_CudaDb *db, cons
     const uint32_t seq = ++mb->seq;
     const auto tq = std::chrono::steady_clock::now();
     auto stamp = [&](int i) { mb->timing_us[i] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tq).count(); };
+    const bool fused = mb->mode == YUME_PDQ_CUDA_MAILBOX_FUSED ||
+                       (mb->mode == YUME_PDQ_CUDA_MAILBOX_AUTO && auto_picks_tensor_rows(db->n_rows, q, threshold));
+    if (fused && db->n_rows > 0 && threshold <= 128) {
+        // ONE launch per rank: the rows-in-M scan posts (root), waits, scans, publishes and collects (root) itself
+        MailboxHook hook{};
+        hook.needles_dev = nullptr;
+        if (mb->rank == root) {
+            if (is_device_ptr(needles))
+                hook.needles_dev = reinterpret_cast<const uint4 *>(needles);
+            else
+                std::memcpy(hook.needles.v, needles, q * 32);
+        }
+        hook.peers = mb->peers;
+        hook.mine = mb->mine;
+        hook.host_out = mb->h_out;
+        hook.world = mb->world;
+        hook.rank = mb->rank;
+        hook.root = root;
+        hook.seq = seq;
+        hook.n_vec = (uint32_t)(2 * q);
+        rc = launch_match_tensor_rows_mailbox(db->planes(), db->n_rows, db->offset, q, threshold, hook, db->sm_count, s);
+        if (rc)
+            return rc;
+        stamp(0);
+        stamp(1);
+        stamp(2);
+        stamp(3);
+    } else {
     if (mb->rank == root) {
         MailboxNeedles arg;
         const uint4 *dev_src = nullptr;
@@ -1411,7 +1389,7 @@ int yume_pdq_cuda_mailbox_scan(YumePDQ_CudaMailbox *mb, YumePDQ_CudaDb *db, cons
     YPDQ_LAUNCH_CHECK();
     stamp(1);
     rc = launch_match(db->planes(), db->n_rows, db->offset, reinterpret_cast<const uint8_t *>(mb->mine->needles), q, threshold,
-                      nullptr, 0, &mb->mine->count, nullptr, MODE_LIST, YUME_PDQ_CUDA_ALGO_AUTO, db->sm_count, s, 0, nullptr);
+                      nullptr, 0, &mb->mine->count[seq & 1u], nullptr, MODE_LIST, YUME_PDQ_CUDA_ALGO_AUTO, db->sm_count, s, 0, nullptr);
     if (rc)
         return rc;
     stamp(2);
@@ -1422,6 +1400,7 @@ int yume_pdq_cuda_mailbox_scan(YumePDQ_CudaMailbox *mb, YumePDQ_CudaDb *db, cons
         YPDQ_LAUNCH_CHECK();
     }
     stamp(3);
+    }
     if (mb->rank != root) {
         // nothing to wait for: this rank's answer travels to the root on the stream; the next query's wait kernel is
         // ordered behind it
@@ -1452,6 +1431,14 @@ int yume_pdq_cuda_mailbox_scan(YumePDQ_CudaMailbox *mb, YumePDQ_CudaDb *db, cons
         return YUME_PDQ_CUDA_E_TIMEOUT;
     if (matched_ranks)
         *matched_ranks = h[1];
+    return 0;
+}
+
+int yume_pdq_cuda_mailbox_set_mode(YumePDQ_CudaMailbox *mb, int mode)
+{
+    if (!mb || mode < YUME_PDQ_CUDA_MAILBOX_AUTO || mode > YUME_PDQ_CUDA_MAILBOX_FUSED)
+        return YUME_PDQ_CUDA_E_INVALID;
+    mb->mode = mode;
     return 0;
 }
 

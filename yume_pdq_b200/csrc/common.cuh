@@ -147,6 +147,88 @@ int launch_match_tensor_rows(DbPlanes rows, size_t n_rows, uint64_t row_offset, 
                              uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
                              unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base = 0);
 
+// ---- peer mailboxes (api.cu; the rows-in-M scan can carry the whole exchange inside its one launch, matcher_tc1.cu) ----
+constexpr int kMailboxMaxWorld = 16;
+constexpr int kMailboxMaxNeedles = 32;
+constexpr unsigned long long kMailboxTimeoutNs = 2000000000ull;    // a peer that never posts must not hang the GPU
+
+struct MailboxMem {
+    uint4 needles[2 * kMailboxMaxNeedles];    // q x 32 B
+    unsigned int seq_in;                      // written by the root after the needles
+    unsigned int count[2];                    // match counter of the local scan of query seq: count[seq & 1]; the other
+                                              // one is zeroed for the next query by whoever publishes this one
+    unsigned int error;                       // a wait timed out
+    unsigned int done;                        // fused scan: CTAs that have finished (reset by the last one)
+    unsigned int pad[3];
+    unsigned int seq_out[kMailboxMaxWorld];   // on the root: written by rank r after result[r]
+    unsigned int result[kMailboxMaxWorld];
+};
+struct MailboxNeedles {
+    uint4 v[2 * kMailboxMaxNeedles];          // 1 KB, by value in the launch parameters: no upload
+};
+struct MailboxPeers {
+    MailboxMem *p[kMailboxMaxWorld];
+};
+// everything the fused scan needs to post (root), wait, publish and collect (root) inside its own launch
+struct MailboxHook {
+    MailboxNeedles needles;                   // root, needles in host memory
+    const uint4 *needles_dev;                 // root, needles in device memory (else nullptr)
+    MailboxPeers peers;
+    MailboxMem *mine;
+    volatile unsigned int *host_out;          // root: mapped host memory {seq, mask of matching ranks, mask of failed ranks}
+    int world, rank, root;
+    uint32_t seq, n_vec;
+};
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// root, one warp: wait (bounded) for every rank's answer of query seq, then {any mask, error mask, seq} to mapped host memory
+__device__ __forceinline__ void mailbox_collect(MailboxMem *mine, int world, uint32_t seq, volatile unsigned int *host_out)
+{
+    const unsigned int lane = threadIdx.x & 31u;
+    unsigned int r = 0, err = 0;
+    if ((int)lane < world) {
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(&mine->seq_out[lane]) != seq) {
+            if (global_ns() - t0 > kMailboxTimeoutNs) {
+                err = 1;
+                break;
+            }
+        }
+        r = *reinterpret_cast<volatile unsigned int *>(&mine->result[lane]);
+    }
+    const unsigned int any = __ballot_sync(0xFFFFFFFFu, (r & 0x7FFFFFFFu) != 0);
+    const unsigned int bad = __ballot_sync(0xFFFFFFFFu, err || (r & 0x80000000u));
+    if (lane == 0) {
+        host_out[1] = any;       // bit r: rank r's shard holds a match
+        host_out[2] = bad;
+        __threadfence_system();
+        host_out[0] = seq;
+    }
+}
+#endif
+
+// the rows-in-M scan with the mailbox exchange folded into its launch (q <= 32; see MailboxHook)
+int launch_match_tensor_rows_mailbox(DbPlanes rows, size_t n_rows, uint64_t row_offset, size_t q, uint32_t threshold,
+                                     const MailboxHook &hook, int sm_count, cudaStream_t s);
+// would ALGO_AUTO send this query to the rows-in-M kernel?  (the fused mailbox scan exists for that kernel only)
+bool auto_picks_tensor_rows(size_t n_rows, size_t q, uint32_t threshold);
+
 int launch_synth_frames(float *frames, size_t n, uint64_t first, uint64_t seed, int kind,
                         cudaStream_t s);
 int launch_synth_pixels(uint8_t *frames, int pixel_format, size_t n, uint64_t first, uint64_t seed,

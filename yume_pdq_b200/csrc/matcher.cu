@@ -262,6 +262,11 @@ match_tiled_kernel(DbPlanes rows, uint64_t n_rows, const uint4 *__restrict__ nee
 }  // namespace
 
 // --------------------------------------------------------------- launcher --
+bool auto_picks_tensor_rows(size_t n_rows, size_t q, uint32_t threshold)
+{
+    return q <= 64 && threshold <= 40 && n_rows >= (q <= 8 ? 1000000u : 500000u);
+}
+
 int launch_match(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
                  size_t q, uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
                  unsigned long long *min_key, int mode, int algo, int sm_count, cudaStream_t s,
@@ -281,7 +286,7 @@ int launch_match(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_
         // is the unpaired full kernel (1024 needles 0.8 ms vs tiled 4.7 ms); the 96-bit prefix bound of the POPC kernels
         // stops filtering once the threshold approaches 48.  A persistent tensor launch costs ~10 us before the first row:
         // small shards stay on the POPC kernel (568k rows x 8: 12.3 us either way, 142k rows: 9.2 vs 10.3).
-        if (q <= 64 && threshold <= 40 && n_rows >= (q <= 8 ? 1000000u : 500000u))
+        if (auto_picks_tensor_rows(n_rows, q, threshold))
             algo = YUME_PDQ_CUDA_ALGO_TENSOR_ROWS;
         else if (q >= (threshold <= 36 ? 14u : 512u) && (q >= 512 || n_rows >= 100000))
             algo = YUME_PDQ_CUDA_ALGO_TENSOR;

@@ -156,7 +156,8 @@ __device__ __forceinline__ bool bar_try_addr_nohint(uint32_t addr, uint32_t pari
 __device__ __noinline__ void x1_verify(uint64_t row, uint32_t needle, DbPlanes rows, const Tc4Sink &sink)
 {
     const uint4 a0 = __ldg(rows.pre + row), a1 = __ldg(rows.suf + row);
-    const uint4 b0 = __ldg(sink.needles_raw + 2 * (size_t)needle), b1 = __ldg(sink.needles_raw + 2 * (size_t)needle + 1);
+    // (the needles of a mailbox query were written during this launch: L2 loads, not the read-only path)
+    const uint4 b0 = __ldcg(sink.needles_raw + 2 * (size_t)needle), b1 = __ldcg(sink.needles_raw + 2 * (size_t)needle + 1);
     const uint32_t dist = hamming256(a0, a1, b0, b1);
     if (dist <= sink.threshold)
         tc4_emit(sink, row, needle, dist);
@@ -209,11 +210,19 @@ __device__ __forceinline__ uint32_t x1_and_tree(const uint32_t (&d)[N])
     }
 }
 
-template <class Cfg>
+struct NoHook {};
+
+// Hook = MailboxHook: the sharded query's whole exchange rides in this launch (api.cu, "peer mailboxes").  The root's
+// CTA 0 stores the needles and then the sequence number into every rank's mailbox over NVLink; every CTA of every rank
+// waits (bounded) for its own mailbox's sequence number and builds its needle tile from the mailbox; the last CTA to
+// finish stores this rank's match count and then the sequence number into the root's mailbox, and on the root also
+// waits for every rank's answer and writes the result to mapped host memory.  No other launch, no collective.
+template <class Cfg, class Hook>
 __global__ void __launch_bounds__(Cfg::THREADS, 1)
-match_rows_m_kernel(DbPlanes rows, uint64_t n_rows, uint32_t q, Tc4Sink sink)
+match_rows_m_kernel(DbPlanes rows, uint64_t n_rows, uint32_t q, Tc4Sink sink, const __grid_constant__ Hook hook)
 {
     constexpr int N = Cfg::N, T = Cfg::T, G = Cfg::G, S = Cfg::S, R = Cfg::R;
+    constexpr bool MB = std::is_same<Hook, MailboxHook>::value;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t *sB = smem;                                                 // needle tile: N rows x 64 B, canonical K-major
     uint8_t *sR = smem + Cfg::NB_BYTES + 256;                           // cp.async ring: one 16-byte cell per (slot, tile, thread)
@@ -223,13 +232,40 @@ match_rows_m_kernel(DbPlanes rows, uint64_t n_rows, uint32_t q, Tc4Sink sink)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t n_units = (n_rows + Cfg::UNIT_ROWS - 1) / Cfg::UNIT_ROWS;
 
+    if constexpr (MB) {
+        if (hook.rank == hook.root && blockIdx.x == 0) {
+            if (threadIdx.x < hook.n_vec) {
+                const uint4 v = hook.needles_dev ? hook.needles_dev[threadIdx.x] : hook.needles.v[threadIdx.x];
+                for (int r = 0; r < hook.world; r++)
+                    hook.peers.p[r]->needles[threadIdx.x] = v;
+            }
+            __threadfence_system();
+            __syncthreads();
+            if ((int)threadIdx.x < hook.world)
+                st_release_sys(&hook.peers.p[threadIdx.x]->seq_in, hook.seq);
+        }
+        if (threadIdx.x == 0) {
+            const unsigned long long t0 = global_ns();
+            while (ld_acquire_sys(&hook.mine->seq_in) != hook.seq) {
+                if (global_ns() - t0 > kMailboxTimeoutNs) {
+                    atomicExch(&hook.mine->error, 1u);
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+    }
     if (threadIdx.x < N) {
         // needle j -> row j of the B tile (needle32: sign and inverse scale of the masked row encoding); its six
         // constant positions carry threshold - popc122(needle), so that D = threshold - hamming122
         const uint32_t j = threadIdx.x;
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (j < q)
-            v = __ldg(sink.needles_raw + 2 * (size_t)j);
+        if (j < q) {
+            if constexpr (MB)      // written by a peer while this kernel was already running: not through the read-only path
+                v = __ldcv(sink.needles_raw + 2 * (size_t)j);
+            else
+                v = __ldg(sink.needles_raw + 2 * (size_t)j);
+        }
         const int32_t p = __popc(v.x & ~X1_BIAS_HASH_BITS) + __popc(v.y) + __popc(v.z) + __popc(v.w);
         const int32_t bias = j < q ? (int32_t)sink.threshold - p : -180;      // padding needles never flag
         uint4 c0 = needle32(v.x);
@@ -458,15 +494,42 @@ match_rows_m_kernel(DbPlanes rows, uint64_t n_rows, uint32_t q, Tc4Sink sink)
     __syncthreads();
     if (warp == Cfg::WARP_MMA)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    if constexpr (MB) {
+        if (warp == 0) {
+            unsigned int last = 0;
+            if (lane == 0) {
+                __threadfence();
+                last = atomicAdd(&hook.mine->done, 1u) == gridDim.x - 1u;
+            }
+            last = __shfl_sync(0xFFFFFFFFu, last, 0);
+            if (last) {
+                MailboxMem *root = hook.peers.p[hook.root];
+                if (lane == 0) {
+                    __threadfence();
+                    hook.mine->done = 0;
+                    const unsigned int cnt = atomicAdd(&hook.mine->count[hook.seq & 1u], 0u);
+                    const unsigned int err = atomicAdd(&hook.mine->error, 0u);
+                    root->result[hook.rank] = (cnt & 0x7FFFFFFFu) | (err ? 0x80000000u : 0u);
+                    hook.mine->count[(hook.seq + 1u) & 1u] = 0;
+                    __threadfence_system();
+                    st_release_sys(&root->seq_out[hook.rank], hook.seq);
+                }
+                __syncwarp();
+                if (hook.rank == hook.root)
+                    mailbox_collect(hook.mine, hook.world, hook.seq, hook.host_out);
+            }
+        }
+    }
 }
 
-template <class Cfg>
-int launch_x1(DbPlanes rows, size_t n_rows, uint32_t q, const Tc4Sink &sink, int sm_count, cudaStream_t s)
+template <class Cfg, class Hook = NoHook>
+int launch_x1(DbPlanes rows, size_t n_rows, uint32_t q, const Tc4Sink &sink, int sm_count, cudaStream_t s, const Hook &hook = Hook())
 {
     const uint64_t n_units = (n_rows + Cfg::UNIT_ROWS - 1) / Cfg::UNIT_ROWS;
     const unsigned grid = (unsigned)std::min<uint64_t>(n_units, (uint64_t)sm_count);
-    YPDQ_CUDA_TRY(cudaFuncSetAttribute(match_rows_m_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-    match_rows_m_kernel<Cfg><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(rows, n_rows, q, sink);
+    YPDQ_CUDA_TRY(
+        cudaFuncSetAttribute(match_rows_m_kernel<Cfg, Hook>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    match_rows_m_kernel<Cfg, Hook><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(rows, n_rows, q, sink, hook);
     YPDQ_LAUNCH_CHECK();
     return 0;
 }
@@ -490,6 +553,23 @@ int launch_match_tensor_rows(DbPlanes rows, size_t n_rows, uint64_t row_offset, 
     if (q <= 32)
         return launch_x1<X1N32>(rows, n_rows, (uint32_t)q, sink, sm_count, s);
     return launch_x1<X1N64>(rows, n_rows, (uint32_t)q, sink, sm_count, s);
+}
+
+// The sharded query in one launch per rank (1 .. 32 needles, n_rows > 0): counts this shard's matches into the mailbox and
+// carries the exchange with the peers (see match_rows_m_kernel).  Every CTA spins on the mailbox, so the grid must be
+// resident at once: it is at most one CTA per SM.
+int launch_match_tensor_rows_mailbox(DbPlanes rows, size_t n_rows, uint64_t row_offset, size_t q, uint32_t threshold,
+                                     const MailboxHook &hook, int sm_count, cudaStream_t s)
+{
+    if (n_rows == 0 || q == 0 || q > (size_t)kMailboxMaxNeedles || threshold > 128)
+        return YUME_PDQ_CUDA_E_INVALID;
+    Tc4Sink sink{nullptr, 0, &hook.mine->count[hook.seq & 1u], nullptr, row_offset, (uint64_t)q, MODE_LIST, 0,
+                 reinterpret_cast<const uint4 *>(hook.mine->needles), threshold};
+    if (q <= 8)
+        return launch_x1<X1N8>(rows, n_rows, (uint32_t)q, sink, sm_count, s, hook);
+    if (q <= 16)
+        return launch_x1<X1N16>(rows, n_rows, (uint32_t)q, sink, sm_count, s, hook);
+    return launch_x1<X1N32>(rows, n_rows, (uint32_t)q, sink, sm_count, s, hook);
 }
 
 }  // namespace ypdq
