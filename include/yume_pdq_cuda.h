@@ -172,6 +172,12 @@ int yume_pdq_cuda_db_auto_state(const YumePDQ_CudaDb *db, int *fallback, uint32_
 int yume_pdq_cuda_db_write_rows(YumePDQ_CudaDb *db, size_t first_local_row, const uint8_t *rows,
                                 size_t n);
 
+/* diagnostic: host-side microsecond stamps of the calling thread's last yume_pdq_hash_smart_kernel call (frame handed to
+ * the copy engine, kernel launched, answer seen, outputs copied out) and, if kernel_clocks7 is not NULL, SM clocks since
+ * its start at which the kernel's finishing CTA was elected, had the tent buffer in shared memory, finished dct stage 1,
+ * stage 2, the median, the hash bits, the gradient sum */
+int yume_pdq_cuda_one_frame_last_timing(double *out4, long long *kernel_clocks7);
+
 /* ---- sharded small-needle query over peer memory (one process per GPU, no collective library) -------------------
  * The multi-GPU form of VulkanMatcher::scan (vulkan.rs:349-406): up to 32 needles on ONE rank, every rank scans its own
  * shard, the root learns which shards matched.  Every rank owns a small mailbox in its HBM that the others map through
@@ -247,6 +253,13 @@ int yume_pdq_cuda_matcher_find_device(YumePDQ_CudaDb *db, const uint8_t *needles
 int yume_pdq_cuda_matcher_find_device_base(YumePDQ_CudaDb *db, const uint8_t *needles_dev, size_t q,
                                            uint32_t threshold, YumePDQ_Match *out_dev, uint32_t cap,
                                            uint32_t *count_dev, int algo, uint32_t needle_base, void *stream);
+/* Same for a batch that is the concatenation of TWO ranges of a longer list with a hole between them -- every rank's
+ * slice of an all-gathered needle batch but the caller's own, which it matched while the gather was in flight: needle j
+ * is reported as needle_base + j for j < split_at and as needle_base + gap + j from split_at on. */
+int yume_pdq_cuda_matcher_find_device_split(YumePDQ_CudaDb *db, const uint8_t *needles_dev, size_t q,
+                                            uint32_t threshold, YumePDQ_Match *out_dev, uint32_t cap,
+                                            uint32_t *count_dev, int algo, uint32_t needle_base, uint32_t split_at,
+                                            uint32_t gap, void *stream);
 
 /* Hash + match in one pipelined call: the flow of examples/end_to_end.rs:224-256 (hash_get_threshold ->
  * visit_dihedrals -> matcher.find for every frame) for a whole batch.  frames n x 512 x 512 f32, host or

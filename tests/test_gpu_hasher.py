@@ -164,6 +164,37 @@ def test_reference_two_function_abi(cuda, oracle, aaa_luma):
     assert cuda.hash_float(aaa_luma)[0] == oq and (cuda.hash(aaa_luma)[1] == oh).all()
 
 
+def test_single_frame_abi_input_kinds(cuda, oracle):
+    """yume_pdq_hash_smart_kernel is one launch that reads the frame while the host is still copying it (pageable
+    input), in place over PCIe (pinned input) or from HBM (device input): all three must give the oracle's
+    hash_get_threshold bit for bit, call after call on the same thread (sequence numbers, the progress counter and
+    the finished-CTA counter carry over), including frames whose content changes completely between calls."""
+    import torch
+    frames = np.concatenate([oracle.synth_frames(5, first_frame=900, kind=1), oracle.synth_frames(3, first_frame=7, kind=0)])
+    frames[6] = 0.0                                   # all-zero frame: PDQF 0, threshold 0, empty hash
+    frames[7] = frames[7][::-1, ::-1]
+    want = [oracle.hash_get_threshold(f) for f in frames]
+    pinned = torch.empty((512, 512), dtype=torch.float32).pin_memory()
+    dev = torch.empty((512, 512), dtype=torch.float32, device="cuda:0")
+    for rnd in range(3):
+        for i, f in enumerate(frames):
+            kind = (i + rnd) % 3
+            if kind == 0:
+                src = np.ascontiguousarray(f)
+            elif kind == 1:
+                pinned.copy_(torch.from_numpy(np.ascontiguousarray(f)))
+                src = pinned
+            else:
+                dev.copy_(torch.from_numpy(np.ascontiguousarray(f)))
+                torch.cuda.synchronize()
+                src = dev
+            q, thr, h, pdqf, buf1 = cuda.hash_get_threshold(src)
+            oq, othr, oh, opdqf = want[i]
+            assert (q, thr) == (oq, othr) and (h == oh).all() and np.array_equal(pdqf, opdqf), (rnd, i, kind)
+            if rnd == 0:
+                assert np.array_equal(buf1, oracle.jarosz_compress(f)), (i, kind)
+
+
 def test_full_size_batch_properties(cuda, kernel, oracle):
     """BASELINE config 2: 4096 frames on the device.  Size-independent properties +
     an oracle spot check on a seeded sample."""

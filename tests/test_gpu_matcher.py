@@ -571,3 +571,30 @@ def test_mailbox_query_one_rank(cuda, oracle, q, n_rows):
             assert mb.scan(db, needles, q, thr, root=0) == want, thr
     mb.close()
     db.close()
+
+
+@pytest.mark.parametrize("algo_name", ["ALGO_AUTO", "ALGO_TILED", "ALGO_EXACT", "ALGO_TENSOR", "ALGO_TENSOR_FULL", "ALGO_TENSOR_ROWS"])
+def test_find_device_split_needle_indices(cuda, oracle, algo_name):
+    """yume_pdq_cuda_matcher_find_device_split: the batch is a longer needle list with a hole cut out (every rank's
+    all-gathered needles but the caller's own); reported indices must be those of the un-cut list, in every kernel."""
+    import torch
+    algo = getattr(cuda, algo_name)
+    rng = np.random.default_rng(99)
+    n_rows = 70_003
+    q_full, lo, hi = (48, 16, 32) if algo_name == "ALGO_TENSOR_ROWS" else (700, 300, 450)     # the hole: [lo, hi)
+    rows = oracle.synth_db(n_rows, first_row=5)
+    full = rng.integers(0, 256, size=(q_full, 32), dtype=np.uint8)
+    for k, r in enumerate(rng.choice(n_rows, size=200, replace=False)):
+        rows[r] = flip_bits(full[(k * 7) % q_full], int(rng.integers(0, 34)), rng)
+    want = [(r, n, d) for r, n, d in match_tuples(oracle.matcher_find(rows, full, 31)) if not lo <= n < hi]
+    assert len(want) > 100 and any(n >= hi for _, n, _ in want) and any(n < lo for _, n, _ in want)
+    cut = np.concatenate([full[:lo], full[hi:]])
+    db = cuda.CudaVectorDatabase(rows)
+    m = cuda.CudaMatcher(db, 31)
+    out = torch.zeros((1 << 12, 16), dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    m.find_device(torch.from_numpy(cut).cuda(), cut.shape[0], out, 1 << 12, cnt, algo=algo, needle_base=1000, split_at=lo, gap=hi - lo)
+    torch.cuda.synchronize()
+    got = out[: int(cnt.item())].cpu().numpy().view(cuda.MATCH_DTYPE).reshape(-1)
+    assert sorted(match_tuples(got)) == sorted((r, n + 1000, d) for r, n, d in want)
+    db.close()

@@ -105,6 +105,19 @@ def main():
             print(f"[{tag}] match 10M x  32768 paired thr={thr}: median {med / 1e3:9.2f} ms  {n * 32768 / med / 1e6:8.3f} Tpairs/s")
             cnt.zero_()
         db.close()
+    if "shard" in what:   # the matcher on the row shards of a 10M-row DB over 8 / 4 / 2 GPUs, needle batches of the N-GPU step
+        tag = os.path.basename(os.environ.get("YUME_PDQ_CUDA_LIB", "default"))
+        out = torch.zeros((1 << 20, 16), dtype=torch.uint8, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        for n, qs in ((1_250_048, (32768, 7 * 32768)), (2_500_096, (32768, 3 * 32768)), (10_000_384, (32768,))):
+            db = yp.CudaVectorDatabase(synthetic_rows=n)
+            m = yp.CudaMatcher(db, 31)
+            for q in qs:
+                needles = torch.from_numpy(rng.integers(0, 256, size=(q, 32), dtype=np.uint8)).cuda()
+                med, best = timeit(lambda: m.find_device(needles, q, out, 1 << 20, cnt), iters=5, warm=1)
+                print(f"[{tag}] match {n:9d} x {q:6d}: median {med / 1e3:9.3f} ms  {n * q / med / 1e6:8.3f} Tpairs/s  hits={int(cnt.item())}")
+                cnt.zero_()
+            db.close()
     if "x1" in what:   # rows-in-M tensor scan only (developer variants: YUME_PDQ_CUDA_LIB=...)
         tag = os.path.basename(os.environ.get("YUME_PDQ_CUDA_LIB", "default"))
         out = torch.zeros((1 << 16, 16), dtype=torch.uint8, device="cuda")

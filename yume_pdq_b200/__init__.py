@@ -104,6 +104,7 @@ SIGNATURES = {
     "yume_pdq_cuda_mailbox_destroy": (C.c_int, [_vp]),
     "yume_pdq_cuda_mailbox_last_timing": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "yume_pdq_cuda_mailbox_set_mode": (C.c_int, [_vp, C.c_int]),
+    "yume_pdq_cuda_one_frame_last_timing": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "yume_pdq_cuda_mailbox_scan": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), _vp]),
     "yume_pdq_cuda_db_auto_state": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_uint32)]),
     "yume_pdq_cuda_db_write_rows": (C.c_int, [_vp, C.c_size_t, _vp, C.c_size_t]),
@@ -116,6 +117,8 @@ SIGNATURES = {
                                                     _vp, C.c_int, _vp]),
     "yume_pdq_cuda_matcher_find_device_base": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _vp, C.c_uint32,
                                                          _vp, C.c_int, C.c_uint32, _vp]),
+    "yume_pdq_cuda_matcher_find_device_split": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _vp, C.c_uint32,
+                                                          _vp, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
     "yume_pdq_cuda_screen_batch": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32, _vp, _vp, _vp, C.c_size_t,
                                              C.POINTER(C.c_size_t), _vp]),
     "yume_pdq_cuda_screen_batch_pixels": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t, C.c_uint32, _vp, _vp, _vp,
@@ -380,8 +383,13 @@ def smart_kernel(device: int = 0) -> CudaKernel:
 
 # ---- drivers over the reference's own two-function C ABI (single frame) ----
 def hash_get_threshold(frame: np.ndarray):
-    """lib.rs:427-455 through ``yume_pdq_hash_smart_kernel`` -> (quality, threshold, hash, pdqf, buf1)."""
-    frame = np.ascontiguousarray(frame, dtype=np.float32).reshape(512, 512)
+    """lib.rs:427-455 through ``yume_pdq_hash_smart_kernel`` -> (quality, threshold, hash, pdqf, buf1).  `frame`: a
+    numpy array (pageable host memory: copied through the library's pinned block while the kernel already runs) or a
+    contiguous f32 torch tensor -- pinned host memory is read in place over PCIe, device memory as is."""
+    if isinstance(frame, np.ndarray) or not hasattr(frame, "data_ptr"):
+        frame = np.ascontiguousarray(frame, dtype=np.float32).reshape(512, 512)
+    elif frame.numel() != 512 * 512 or frame.element_size() != 4:
+        raise ValueError("frame must hold 512 x 512 f32")
     thr = C.c_float(0.0)
     out = np.zeros(32, dtype=np.uint8)
     buf1 = np.zeros((128, 128), dtype=np.float32)
@@ -567,9 +575,18 @@ class CudaMatcher:
             return out[: k.value].copy()
 
     def find_device(self, needles_dev, q: int, out_dev, cap: int, count_dev, algo: int = ALGO_AUTO,
-                    stream=None, needle_base: int = 0):
+                    stream=None, needle_base: int = 0, split_at=None, gap: int = 0):
         """Asynchronous device-side scan (torch CUDA tensors or raw device pointers); ``needle_base`` is
-        added to the reported needle indices (chunked callers)."""
+        added to the reported needle indices (chunked callers); with ``split_at`` the batch is the concatenation of two
+        ranges of a longer list and needles from ``split_at`` on are reported ``gap`` higher
+        (yume_pdq_cuda_matcher_find_device_split)."""
+        if split_at is not None:
+            _check(lib.yume_pdq_cuda_matcher_find_device_split(self.haystack._h, _ptr(needles_dev), q,
+                                                               self.threshold, _ptr(out_dev), cap, _ptr(count_dev),
+                                                               algo, needle_base, split_at, gap,
+                                                               _stream(stream or self.stream)),
+                   "matcher_find_device_split")
+            return
         _check(lib.yume_pdq_cuda_matcher_find_device_base(self.haystack._h, _ptr(needles_dev), q,
                                                           self.threshold, _ptr(out_dev), cap, _ptr(count_dev),
                                                           algo, needle_base, _stream(stream or self.stream)),

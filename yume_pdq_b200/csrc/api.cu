@@ -237,6 +237,63 @@ __global__ void dihedral_states_kernel(const float *__restrict__ pdqf, float *__
     }
 }
 
+// the single-frame latency path's buffers, per (host thread, device): the tent buffer, the finished-CTA counter and the
+// frame in device memory, results + staging block in pinned (mapped) host memory
+#ifndef YPDQ_ONE_FRAME_PARTS
+#define YPDQ_ONE_FRAME_PARTS 4
+#endif
+struct OneFrameCtx {
+    int device = -1;
+    float *buf1_dev = nullptr;
+    unsigned int *done = nullptr;
+    OneFrameOut *out = nullptr;
+    float *stage = nullptr;
+    float *frame_dev = nullptr;
+    uint32_t seq = 0;
+    double stamps_us[8] = {0};    // host-side stamps of the last call (diagnostic)
+    int init(int device_)
+    {
+        if (out)
+            return 0;
+        device = device_;
+        void *d = nullptr, *h = nullptr;
+        if (cudaMalloc(&d, 128 * 128 * 4 + 256 + 512 * 512 * 4) != cudaSuccess || cudaMemset(d, 0, 128 * 128 * 4 + 256) != cudaSuccess ||
+            cudaMallocHost(&h, sizeof(OneFrameOut) + 512 * 512 * 4) != cudaSuccess) {
+            (void)cudaGetLastError();
+            if (d)
+                cudaFree(d);
+            return YUME_PDQ_CUDA_E_NOMEM;
+        }
+        std::memset(h, 0, sizeof(OneFrameOut));
+        buf1_dev = static_cast<float *>(d);
+        done = reinterpret_cast<unsigned int *>(static_cast<uint8_t *>(d) + 128 * 128 * 4);
+        frame_dev = reinterpret_cast<float *>(static_cast<uint8_t *>(d) + 128 * 128 * 4 + 256);
+        out = static_cast<OneFrameOut *>(h);
+        stage = reinterpret_cast<float *>(static_cast<uint8_t *>(h) + sizeof(OneFrameOut));
+        return 0;
+    }
+    ~OneFrameCtx()
+    {
+        if (!out)
+            return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cudaSetDevice(device) != cudaSuccess) {
+            (void)cudaGetLastError();   // runtime already torn down at process exit
+            return;
+        }
+        cudaFree(buf1_dev);
+        cudaFreeHost(out);
+        if (cur >= 0)
+            cudaSetDevice(cur);
+        (void)cudaGetLastError();
+    }
+};
+OneFrameCtx &tls_one_frame(int device)
+{
+    static thread_local OneFrameCtx c[kMaxDevices];
+    return c[(unsigned)device % kMaxDevices];
+}
+
 int default_device()
 {
     const char *e = std::getenv("YUME_PDQ_CUDA_DEVICE");
@@ -307,49 +364,91 @@ float yume_pdq_hash_smart_kernel(const float *input, float *threshold, uint8_t *
     const int device = default_device();
     if (!input || !output || !buf1 || !pdqf || ensure_device(device) != 0)
         return nan;
-    // hash_get_threshold, src/lib.rs:427-455, as a latency path: ONE upload of the frame, the per-stage kernels
-    // (the tent filter spreads over 128 CTAs; the fused batch kernel would stream the frame through a single CTA),
-    // ONE download of {buf1, pdqf, threshold, quality, hash}, one synchronisation.
-    struct Out {
-        float buf1[128 * 128];
-        float pdqf[256];
-        float thr, quality, gradient, thr_avx2;
-        uint8_t hash[32];
-    };
-    Scratch &sc = tls_scratch(2, device);
-    if (sc.reserve(device, 512 * 512 * 4 + sizeof(Out) + 512, sizeof(Out)) != 0)
+    // hash_get_threshold, src/lib.rs:427-455, as a LATENCY path (the reference quotes 81 us per ctypes call,
+    // README.md:170-173).  Pageable input: the host moves the frame into pinned memory a quarter at a time and hands
+    // every quarter to the copy engine as soon as it is there (the DMA of one overlaps the memcpy of the next); pinned
+    // input: one DMA; device input: none.  Then ONE launch (hasher.cu hash_one_kernel) that writes {buf1, pdqf,
+    // threshold, quality, hash} and finally a sequence number straight into mapped host memory, which this thread
+    // polls: no D2H copy, no stream synchronisation.
+    OneFrameCtx &cx = tls_one_frame(device);
+    if (cx.init(device) != 0)
         return nan;
     cudaStream_t s = nullptr;
-    const float *d_in = input;
-    Out *d_out = reinterpret_cast<Out *>(sc.dev);
-    if (!is_device_ptr(input)) {
-        float *d_frame = reinterpret_cast<float *>(static_cast<uint8_t *>(sc.dev) + align_up(sizeof(Out), 256));
-        if (cudaMemcpyAsync(d_frame, input, 512 * 512 * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) {
-            (void)cudaGetLastError();
-            return nan;
-        }
-        d_in = d_frame;
+    const float *frame = cx.frame_dev;
+    const auto tq = std::chrono::steady_clock::now();
+    auto stamp = [&](int i) { cx.stamps_us[i] = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tq).count(); };
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, input) != cudaSuccess) {
+        (void)cudaGetLastError();
+        at.type = cudaMemoryTypeUnregistered;
     }
-    // README.md:164-168 prints the AVX2 kernel's bisection threshold; opt in with YUME_PDQ_CUDA_THRESHOLD=avx2
-    const char *style = std::getenv("YUME_PDQ_CUDA_THRESHOLD");
-    const bool avx2_style = style && std::strcmp(style, "avx2") == 0;
-    if (launch_jarosz(d_in, 1, d_out->buf1, s) != 0 || launch_dct2d(d_out->buf1, 1, d_out->pdqf, s) != 0 ||
-        launch_quantize(d_out->pdqf, 1, &d_out->thr, d_out->hash, s) != 0 ||
-        launch_gradients(d_out->pdqf, 1, &d_out->gradient, &d_out->quality, s) != 0 ||
-        (avx2_style && launch_avx2_style_threshold(d_out->pdqf, &d_out->thr_avx2, s) != 0))
-        return nan;
-    Out *h = reinterpret_cast<Out *>(sc.pin);
-    if (cudaMemcpyAsync(h, d_out, sizeof(Out), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaStreamSynchronize(s) != cudaSuccess) {
+    cudaError_t ce = cudaSuccess;
+    if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) {
+        frame = input;
+    } else if (at.type == cudaMemoryTypeHost) {
+        ce = cudaMemcpyAsync(cx.frame_dev, input, 512 * 512 * sizeof(float), cudaMemcpyHostToDevice, s);
+    } else {
+        constexpr int parts = YPDQ_ONE_FRAME_PARTS;
+        constexpr size_t part = 512 * 512 / parts;      // floats
+        for (int c = 0; c < parts && ce == cudaSuccess; c++) {
+            std::memcpy(cx.stage + c * part, input + c * part, part * sizeof(float));
+            ce = cudaMemcpyAsync(cx.frame_dev + c * part, cx.stage + c * part, part * sizeof(float), cudaMemcpyHostToDevice, s);
+        }
+    }
+    if (ce != cudaSuccess) {
         (void)cudaGetLastError();
         return nan;
     }
+    stamp(0);
+    // README.md:164-168 prints the AVX2 kernel's bisection threshold; opt in with YUME_PDQ_CUDA_THRESHOLD=avx2
+    const char *style = std::getenv("YUME_PDQ_CUDA_THRESHOLD");
+    const bool avx2_style = style && std::strcmp(style, "avx2") == 0;
+    OneFrameOut *h = cx.out;
+    const uint32_t seq = ++cx.seq;
+    if (launch_hash_one(frame, cx.buf1_dev, cx.done, h, seq, avx2_style, s) != 0)
+        return nan;
+    stamp(1);
+    volatile unsigned int *flag = &h->seq;
+    const auto t0 = std::chrono::steady_clock::now();
+    uint32_t spins = 0;
+    while (*flag != seq) {
+        if ((++spins & 0x3FFFu) == 0) {
+            if (cudaStreamQuery(s) != cudaErrorNotReady)      // finished (or failed) without the store becoming visible
+                break;
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5))
+                break;
+        }
+    }
+    if (*flag != seq) {
+        if (cudaStreamSynchronize(s) != cudaSuccess || *flag != seq) {
+            (void)cudaGetLastError();
+            return nan;
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    stamp(2);
     std::memcpy(buf1, h->buf1, sizeof h->buf1);
     std::memcpy(pdqf, h->pdqf, sizeof h->pdqf);
     std::memcpy(output, h->hash, 32);
     if (threshold)
         *threshold = avx2_style ? h->thr_avx2 : h->thr;
+    stamp(3);
     return h->quality;
+}
+
+/* diagnostic: host-side microsecond stamps of this thread's last yume_pdq_hash_smart_kernel call -- frame handed to the
+ * copy engine, kernel launched, answer seen, outputs copied */
+int yume_pdq_cuda_one_frame_last_timing(double *out4, long long *kernel_clocks7)
+{
+    if (!out4)
+        return YUME_PDQ_CUDA_E_INVALID;
+    const OneFrameCtx &cx = tls_one_frame(default_device());
+    for (int i = 0; i < 4; i++)
+        out4[i] = cx.stamps_us[i];
+    if (kernel_clocks7)
+        for (int i = 0; i < 7; i++)
+            kernel_clocks7[i] = cx.out ? cx.out->trace[i + 1] - cx.out->trace[0] : 0;
+    return 0;
 }
 
 bool yume_pdq_visit_dihedrals_smart_kernel(void *ctx, float threshold, uint8_t *output, float *pdqf,
@@ -1032,6 +1131,20 @@ int yume_pdq_cuda_matcher_find_device_base(YumePDQ_CudaDb *db, const uint8_t *ne
         return rc;
     return launch_match(db->planes(), db->n_rows, db->offset, needles_dev, q, threshold, out_dev, cap,
                         count_dev, nullptr, MODE_LIST, algo, db->sm_count, (cudaStream_t)stream, needle_base, db->stats);
+}
+
+int yume_pdq_cuda_matcher_find_device_split(YumePDQ_CudaDb *db, const uint8_t *needles_dev, size_t q,
+                                            uint32_t threshold, YumePDQ_Match *out_dev, uint32_t cap,
+                                            uint32_t *count_dev, int algo, uint32_t needle_base, uint32_t split_at,
+                                            uint32_t gap, void *stream)
+{
+    if (!db || !needles_dev || !count_dev || q == 0 || (cap && !out_dev))
+        return YUME_PDQ_CUDA_E_INVALID;
+    int rc = ensure_device(db->device);
+    if (rc)
+        return rc;
+    return launch_match(db->planes(), db->n_rows, db->offset, needles_dev, q, threshold, out_dev, cap, count_dev, nullptr,
+                        MODE_LIST, algo, db->sm_count, (cudaStream_t)stream, NeedleMap(needle_base, split_at, gap), db->stats);
 }
 
 int yume_pdq_cuda_screen_batch(YumePDQ_CudaDb *db, const float *frames, size_t n, uint32_t threshold,

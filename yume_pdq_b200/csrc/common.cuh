@@ -1,6 +1,7 @@
 // common.cuh -- shared helpers for the sm_100a kernels and the C ABI.
 #pragma once
 #include <cuda_runtime.h>
+#include <cstddef>
 #include <stdint.h>
 
 #include <atomic>
@@ -123,29 +124,43 @@ __device__ __forceinline__ uint32_t reserve_matches(uint32_t *count, uint32_t n)
     return pos;
 }
 #endif
+// How a launch's needle index j is reported (LIST mode): base + j, plus `gap` from index `split_at` on -- a batch that is
+// a chunk of a longer list (base), possibly the concatenation of two ranges of it with a hole between them (the
+// all-gathered needles of every rank but the caller's own)
+struct NeedleMap {
+    uint32_t base = 0, split_at = 0xFFFFFFFFu, gap = 0;
+    NeedleMap() = default;
+    NeedleMap(uint32_t base_) : base(base_) {}
+    NeedleMap(uint32_t base_, uint32_t split_at_, uint32_t gap_) : base(base_), split_at(split_at_), gap(gap_) {}
+#ifdef __CUDACC__
+    __host__ __device__
+#endif
+    uint32_t operator()(uint32_t j) const { return base + j + (j >= split_at ? gap : 0u); }
+};
+
 int launch_match(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
                  size_t q, uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
                  unsigned long long *min_key, int mode, int algo, int sm_count, cudaStream_t s,
-                 uint32_t needle_base = 0, MatchStats *stats = nullptr);
+                 NeedleMap needle_base = NeedleMap(), MatchStats *stats = nullptr);
 
 int launch_match_tensor(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
                         size_t q, uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
-                        unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base = 0);
+                        unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, NeedleMap needle_base = NeedleMap());
 
 int launch_match_tensor4(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
                          size_t q, uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
-                         unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base = 0,
+                         unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, NeedleMap needle_base = NeedleMap(),
                          int prefix = -1);
 
 int launch_match_tensor4x2(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
                            size_t q, uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
                            unsigned long long *min_key, int mode, int sm_count, cudaStream_t s,
-                           uint32_t needle_base = 0, MatchStats *stats = nullptr);
+                           NeedleMap needle_base = NeedleMap(), MatchStats *stats = nullptr);
 
 // 1 .. 32 needles: database rows in the M dimension, operand A written to tensor memory from registers (matcher_tc1.cu)
 int launch_match_tensor_rows(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles, size_t q,
                              uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
-                             unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base = 0);
+                             unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, NeedleMap needle_base = NeedleMap());
 
 // ---- peer mailboxes (api.cu; the rows-in-M scan can carry the whole exchange inside its one launch, matcher_tc1.cu) ----
 constexpr int kMailboxMaxWorld = 16;
@@ -228,6 +243,20 @@ int launch_match_tensor_rows_mailbox(DbPlanes rows, size_t n_rows, uint64_t row_
                                      const MailboxHook &hook, int sm_count, cudaStream_t s);
 // would ALGO_AUTO send this query to the rows-in-M kernel?  (the fused mailbox scan exists for that kernel only)
 bool auto_picks_tensor_rows(size_t n_rows, size_t q, uint32_t threshold);
+
+// ---- one frame, latency path (hasher.cu hash_one_kernel; api.cu yume_pdq_hash_smart_kernel) ----
+struct OneFrameOut {                      // mapped host memory, written by the kernel
+    float buf1[128 * 128];
+    float pdqf[256];
+    float thr, quality, gradient, thr_avx2;
+    uint8_t hash[32];
+    unsigned int seq;                     // written last
+    unsigned int pad[3];
+    long long trace[8];                   // diagnostic, SM clocks of the finishing CTA: start, elected, tent buffer staged,
+                                          // dct stage 1, stage 2, median + gradients, hash bits
+};
+int launch_hash_one(const float *frame, float *buf1_dev, unsigned int *done, OneFrameOut *out, uint32_t seq, bool avx2_style,
+                    cudaStream_t s);
 
 int launch_synth_frames(float *frames, size_t n, uint64_t first, uint64_t seed, int kind,
                         cudaStream_t s);

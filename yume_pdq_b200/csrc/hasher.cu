@@ -617,8 +617,8 @@ int upload_luts()
 // point where a mean-of-the-residual-side bisection stops, anywhere in [sorted[127], sorted[128]).  The hash bits are
 // the same; callers that print the float see a different number (README.md:164-168: 12.554 where Torben gives
 // 11.907).  Lanes 0..7 of one warp play the eight lanes of a __m256, in the reference's operation order.
-__global__ void __launch_bounds__(32)
-avx2_style_threshold_kernel(const float *__restrict__ pdqf, float *__restrict__ out)
+// one full warp; the result is valid in lane 0
+__device__ float avx2_style_threshold(const float *pdqf)
 {
     const unsigned full = 0xffffffffu;
     const int l = threadIdx.x & 7;
@@ -668,8 +668,195 @@ avx2_style_threshold_kernel(const float *__restrict__ pdqf, float *__restrict__ 
             break;
         }
     }
+    return guess;
+}
+
+__global__ void __launch_bounds__(32)
+avx2_style_threshold_kernel(const float *__restrict__ pdqf, float *__restrict__ out)
+{
+    const float guess = avx2_style_threshold(pdqf);
     if (threadIdx.x == 0)
         *out = guess;
+}
+
+// ---------------------------------------------------------------- one frame, latency path --
+// hash_get_threshold (src/lib.rs:427-455) for ONE frame in ONE launch, built for the latency of the reference's
+// single-frame C ABI (yume_pdq_hash_smart_kernel) rather than for throughput:
+//   * 128 CTAs, one per row of the 128 x 128 tent buffer (the fused batch kernel streams a frame through one CTA);
+//   * the last CTA to finish (device-scope counter) stages the tent buffer in shared memory and runs dct2d, the lower
+//     median, the gradient sum and the hash bits exactly as the per-stage kernels do;
+//   * results go straight to mapped host memory, then the sequence number: the host polls it, no D2H copy, no stream
+//     synchronisation.
+// (Reading the frame in place from pinned host memory was measured too: 1 MiB of 16-byte loads over PCIe takes ~40 us,
+// 26 GB/s, where the copy engine needs 19 us; and letting the kernel chase the host's copy chunk by chunk slowed the
+// host's copy down to 150 us -- the frame is therefore always in device memory here.)
+// SM clock for the diagnostic trace; the memory clobber keeps the read where it is written (between barriers)
+__device__ __forceinline__ long long one_clock()
+{
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+    return t;
+}
+
+constexpr int ONE_T = 512;      // threads per CTA: the tent row uses 128 of them, the finishing CTA all
+
+__global__ void __launch_bounds__(ONE_T)
+hash_one_kernel(const float *__restrict__ frame, float *buf1_dev, unsigned int *done, OneFrameOut *out, uint32_t seq,
+                int avx2_style)
+{
+    extern __shared__ __align__(16) float s_b[];      // finishing CTA: the 128 x 128 tent buffer, later the gradient terms
+    __shared__ HashSmem sm;
+    __shared__ unsigned int s_last;
+    const int tid = threadIdx.x, oi = blockIdx.x, lane = tid & 31;
+    const long long t_start = one_clock();
+    if (tid < 128) {
+        float sum = 0.0f;      // row 127 and column 127: zero padding (x86.rs:756-757, lib.rs:296-297)
+        if (oi < 127) {
+            // columns 4j .. 4j+3 from this thread's load, 4j+4 .. 4j+6 from the right neighbour's
+            const float *row = frame + (size_t)(4 * oi + 2) * 512 + 4 * tid;
+            float4 a[5], b[5];
+#pragma unroll
+            for (int r = 0; r < 5; r++)
+                a[r] = __ldg(reinterpret_cast<const float4 *>(row + r * 512));
+#pragma unroll
+            for (int r = 0; r < 5; r++) {
+                b[r].x = __shfl_down_sync(0xffffffffu, a[r].x, 1);
+                b[r].y = __shfl_down_sync(0xffffffffu, a[r].y, 1);
+                b[r].z = __shfl_down_sync(0xffffffffu, a[r].z, 1);
+            }
+            if (lane == 31 && tid < 127) {
+#pragma unroll
+                for (int r = 0; r < 5; r++)
+                    b[r] = __ldg(reinterpret_cast<const float4 *>(row + r * 512 + 4));
+            }
+            if (tid < 127) {
+                sum = tent_row<1>(sum, Win5{a[0].z, a[0].w, b[0].x, b[0].y, b[0].z});
+                sum = tent_row<2>(sum, Win5{a[1].z, a[1].w, b[1].x, b[1].y, b[1].z});
+                sum = tent_row<3>(sum, Win5{a[2].z, a[2].w, b[2].x, b[2].y, b[2].z});
+                sum = tent_row<4>(sum, Win5{a[3].z, a[3].w, b[3].x, b[3].y, b[3].z});
+                sum = tent_row<5>(sum, Win5{a[4].z, a[4].w, b[4].x, b[4].y, b[4].z});
+            }
+        }
+        buf1_dev[oi * 128 + tid] = sum;
+        out->buf1[oi * 128 + tid] = sum;
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0)
+        s_last = atomicAdd(done, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (!s_last)
+        return;
+    if (tid == 0) {
+        *done = 0;
+        out->trace[0] = t_start;
+        out->trace[1] = one_clock();
+    }
+    __threadfence();
+    {
+        const float4 *g4 = reinterpret_cast<const float4 *>(buf1_dev);
+        float4 *s4 = reinterpret_cast<float4 *>(s_b);
+        float4 v[8];      // 128 x 128 / 4 / 512 = 8 loads per thread, all in flight
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            v[i] = __ldcg(g4 + tid + i * ONE_T);
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            s4[tid + i * ONE_T] = v[i];
+    }
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(g_dt);
+        float4 *dst = reinterpret_cast<float4 *>(sm.dt);
+        if (tid < 127 * 4)
+            dst[tid] = src[tid];
+    }
+    __syncthreads();
+    if (tid == 0)
+        out->trace[2] = one_clock();
+    {
+        // dct2d stage 1 as in dct2d_kernel, the 16 DCT rows split over four thread groups: thread (j, kq) carries rows
+        // 4 kq .. 4 kq + 3 of column j -- every (k, j, partial sum) chain adds the same terms in the same order
+        const int j = (tid & 127) < 127 ? (tid & 127) : 126, kq = tid >> 7;
+        const float *b = s_b + j;
+        const float *dq = sm.dt + 4 * kq;
+        float acc[4][4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+                acc[k][r] = 0.0f;
+        auto upd = [&](int k2, int r, float bv) {
+            const float4 d = *reinterpret_cast<const float4 *>(dq + k2 * 16);
+            acc[0][r] = __fadd_rn(acc[0][r], __fmul_rn(d.x, bv));
+            acc[1][r] = __fadd_rn(acc[1][r], __fmul_rn(d.y, bv));
+            acc[2][r] = __fadd_rn(acc[2][r], __fmul_rn(d.z, bv));
+            acc[3][r] = __fadd_rn(acc[3][r], __fmul_rn(d.w, bv));
+        };
+#pragma unroll 4
+        for (int k2 = 0; k2 < 124; k2 += 4) {
+            upd(k2 + 0, 0, b[(k2 + 0) * 128]);
+            upd(k2 + 1, 1, b[(k2 + 1) * 128]);
+            upd(k2 + 2, 2, b[(k2 + 2) * 128]);
+            upd(k2 + 3, 3, b[(k2 + 3) * 128]);
+        }
+        upd(124, 0, b[124 * 128]);
+        upd(125, 1, b[125 * 128]);
+        upd(126, 2, b[126 * 128]);
+        if ((tid & 127) < 127) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                sm.t[(4 * kq + k) * TSTRIDE + j] = __fadd_rn(__fadd_rn(__fadd_rn(acc[k][0], acc[k][1]), acc[k][2]), acc[k][3]);
+        }
+    }
+    __syncthreads();
+    if (tid == 0)
+        out->trace[3] = one_clock();
+    if (tid < HT)
+        dct_stage2(sm, tid);
+    __syncthreads();
+    if (tid == 0)
+        out->trace[4] = one_clock();
+    if (tid < 256)
+        out->pdqf[tid] = sm.p[tid];
+    // sum_of_gradients (mod.rs:617-642): the 480 terms in parallel, then ONE thread adds them in the reference's order
+    if (tid < 240)
+        s_b[tid] = fabsf(__fsub_rn(sm.p[tid], sm.p[tid + 16]));                              // (i, j) - (i + 1, j), i < 15
+    else if (tid < 480) {
+        const int t = tid - 240, i = t / 15, j = t - 15 * i;
+        s_b[tid] = fabsf(__fsub_rn(sm.p[i * 16 + j], sm.p[i * 16 + j + 1]));                 // (i, j) - (i, j + 1), j < 15
+    }
+    __syncthreads();
+    if (tid < 32) {
+        const float med = warp_lower_median(sm.p, 0, tid);
+        if (tid == 0) {
+            sm.thr[0] = med;
+            out->thr = med;
+            out->trace[5] = one_clock();
+        }
+    } else if (tid == 32) {
+        float g = 0.0f;
+#pragma unroll 16
+        for (int t = 0; t < 480; t++)
+            g = __fadd_rn(g, s_b[t]);
+        out->gradient = g;
+        out->quality = adjust_quality(g);
+        long long t;
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "f"(g) : "memory");
+        out->trace[7] = t;
+    } else if (tid >= 64 && tid < 96 && avx2_style) {
+        const float t = avx2_style_threshold(sm.p);
+        if (tid == 64)
+            out->thr_avx2 = t;
+    }
+    __syncthreads();
+    if (tid < HT)
+        write_hash_bits(sm.p, 0, sm.thr[0], out->hash, tid);
+    if (tid == 0)
+        out->trace[6] = one_clock();
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0)
+        st_release_sys(&out->seq, seq);
 }
 
 }  // namespace
@@ -735,6 +922,25 @@ int launch_cvt_luma8f(const void *pixels, int pixel_format, size_t n_pixels, con
 int launch_avx2_style_threshold(const float *pdqf, float *out, cudaStream_t s)
 {
     avx2_style_threshold_kernel<<<1, 32, 0, s>>>(pdqf, out);
+    YPDQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_hash_one(const float *frame, float *buf1_dev, unsigned int *done, OneFrameOut *out, uint32_t seq, bool avx2_style,
+                    cudaStream_t s)
+{
+    int rc = upload_luts();
+    if (rc)
+        return rc;
+    constexpr int dyn = 128 * 128 * 4;
+    static std::atomic<int> attr_set[64];
+    int dev = 0;
+    YPDQ_CUDA_TRY(cudaGetDevice(&dev));
+    if (!attr_set[dev & 63].load(std::memory_order_acquire)) {
+        YPDQ_CUDA_TRY(cudaFuncSetAttribute(hash_one_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+        attr_set[dev & 63].store(1, std::memory_order_release);
+    }
+    hash_one_kernel<<<128, ONE_T, dyn, s>>>(frame, buf1_dev, done, out, seq, avx2_style ? 1 : 0);
     YPDQ_LAUNCH_CHECK();
     return 0;
 }

@@ -75,7 +75,7 @@ struct Sink {
     uint64_t row_offset;
     uint64_t q;
     int mode;
-    uint32_t needle_base;   // added to reported needle indices (LIST mode): pipelined callers match in chunks
+    NeedleMap needle_base;   // added to reported needle indices (LIST mode): pipelined callers match in chunks
 };
 
 // one hit from divergent code
@@ -88,7 +88,7 @@ __device__ __forceinline__ void emit_single(const Sink &k, uint64_t local_row, u
     } else if (pos < k.cap) {
         YumePDQ_Match m;
         m.row = local_row + k.row_offset;
-        m.needle = needle + k.needle_base;
+        m.needle = k.needle_base(needle);
         m.dist = dist;
         k.out[pos] = m;
     }
@@ -116,7 +116,7 @@ __device__ __forceinline__ void emit_ballot(const Sink &k, bool hit, uint64_t lo
             if (pos < k.cap) {
                 YumePDQ_Match m;
                 m.row = local_row + k.row_offset;
-                m.needle = needle + k.needle_base;
+                m.needle = k.needle_base(needle);
                 m.dist = dist;
                 k.out[pos] = m;
             }
@@ -270,7 +270,7 @@ bool auto_picks_tensor_rows(size_t n_rows, size_t q, uint32_t threshold)
 int launch_match(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles,
                  size_t q, uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
                  unsigned long long *min_key, int mode, int algo, int sm_count, cudaStream_t s,
-                 uint32_t needle_base, MatchStats *stats)
+                 NeedleMap needle_base, MatchStats *stats)
 {
     if (n_rows == 0 || q == 0)
         return 0;

@@ -128,7 +128,7 @@ struct TcSink {
     uint64_t row_offset;
     uint64_t q;
     int mode;
-    uint32_t needle_base;   // added to reported needle indices (LIST mode): pipelined callers match in chunks
+    NeedleMap needle_base;   // added to reported needle indices (LIST mode): pipelined callers match in chunks
 };
 
 __device__ __forceinline__ void tc_emit(const TcSink &k, uint64_t local_row, uint32_t needle, uint32_t dist)
@@ -139,7 +139,7 @@ __device__ __forceinline__ void tc_emit(const TcSink &k, uint64_t local_row, uin
     } else if (pos < k.cap) {
         YumePDQ_Match m;
         m.row = local_row + k.row_offset;
-        m.needle = needle + k.needle_base;
+        m.needle = k.needle_base(needle);
         m.dist = dist;
         k.out[pos] = m;
     }
@@ -315,7 +315,7 @@ match_tensor_kernel(DbPlanes rows, uint64_t n_rows, const uint8_t *__restrict__ 
 
 int launch_match_tensor(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles, size_t q,
                         uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
-                        unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base)
+                        unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, NeedleMap needle_base)
 {
     if (n_rows == 0 || q == 0)
         return 0;

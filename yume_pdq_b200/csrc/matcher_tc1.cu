@@ -539,7 +539,7 @@ int launch_x1(DbPlanes rows, size_t n_rows, uint32_t q, const Tc4Sink &sink, int
 // 1 .. 64 needles, any threshold up to 128 (the prefix filter only thins the pairs; it is useful up to ~48)
 int launch_match_tensor_rows(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles, size_t q,
                              uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
-                             unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base)
+                             unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, NeedleMap needle_base)
 {
     if (n_rows == 0 || q == 0)
         return 0;

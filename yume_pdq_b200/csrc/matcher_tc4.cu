@@ -464,7 +464,7 @@ static int launch_tc4(DbPlanes rows, size_t n_rows, const uint8_t *needles, size
 // 1: 128-bit prefix filter
 int launch_match_tensor4(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles, size_t q,
                          uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
-                         unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base,
+                         unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, NeedleMap needle_base,
                          int prefix)
 {
     if (n_rows == 0 || q == 0)

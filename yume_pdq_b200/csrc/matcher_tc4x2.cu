@@ -138,7 +138,12 @@ constexpr uint32_t X2_ROW_BIAS = 0x00777777u, X2_NEEDLE_BIAS = 0x00477777u;   //
 #define X2_PREFETCH_UNITS_CFG 6
 #endif
 constexpr uint32_t X2_PREFETCH_UNITS = X2_PREFETCH_UNITS_CFG;
-constexpr int X2_MIN_CHUNK_TILES = 32;               // needle tiles per work unit, at least (amortises the row expansion)
+#ifndef X2_MIN_CHUNK_TILES_CFG
+#define X2_MIN_CHUNK_TILES_CFG 32
+#define X2_UNITS_PER_SM_CFG 64
+#endif
+constexpr int X2_MIN_CHUNK_TILES = X2_MIN_CHUNK_TILES_CFG;   // needle tiles per work unit, at least (amortises the row expansion)
+constexpr int X2_UNITS_PER_SM = X2_UNITS_PER_SM_CFG;         // work units per SM a small shard is cut into
 
 // block-scaled instruction descriptor: A = B = e2m1, both K-major, ue8m0 scales, dense K = 64
 constexpr uint32_t X2_IDESC = (1u << 7) | (1u << 10) | ((uint32_t)(X2_N >> 3) << 17) | (1u << 23) | ((uint32_t)(X2_M >> 4) << 24);
@@ -680,7 +685,7 @@ match_tensor4x2_kernel(DbPlanes rows, uint64_t n_rows, const uint8_t *__restrict
 // 128 / 122-bit prefix filter, two rows per accumulator column (threshold <= 60; candidates verified with POPC)
 int launch_match_tensor4x2(DbPlanes rows, size_t n_rows, uint64_t row_offset, const uint8_t *needles, size_t q,
                            uint32_t threshold, YumePDQ_Match *out, uint32_t cap, uint32_t *count,
-                           unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, uint32_t needle_base,
+                           unsigned long long *min_key, int mode, int sm_count, cudaStream_t s, NeedleMap needle_base,
                            MatchStats *stats)
 {
     if (n_rows == 0 || q == 0)
@@ -695,7 +700,7 @@ int launch_match_tensor4x2(DbPlanes rows, size_t n_rows, uint64_t row_offset, co
     X2Units units;
     units.n_stiles = (n_rows + X2_ROWS - 1) / X2_ROWS;
     units.n_mtiles = n_mtiles;
-    const uint64_t want_chunks = (64ull * (uint64_t)sm_count + units.n_stiles - 1) / units.n_stiles;
+    const uint64_t want_chunks = ((uint64_t)X2_UNITS_PER_SM * (uint64_t)sm_count + units.n_stiles - 1) / units.n_stiles;
     const uint64_t max_chunks = std::max<uint64_t>(1, n_mtiles / X2_MIN_CHUNK_TILES);
     const uint32_t n_chunks = (uint32_t)std::max<uint64_t>(1, std::min(want_chunks, max_chunks));
     units.chunk_tiles = (n_mtiles + n_chunks - 1) / n_chunks;

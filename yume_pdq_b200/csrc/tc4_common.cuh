@@ -120,7 +120,7 @@ struct Tc4Sink {
     uint64_t row_offset;
     uint64_t q;
     int mode;
-    uint32_t needle_base;   // added to reported needle indices (LIST mode): pipelined callers match in chunks
+    NeedleMap needle_base;   // added to reported needle indices (LIST mode): pipelined callers match in chunks
     const uint4 *needles_raw;   // q x 32 B: prefix-filter candidates are verified on the packed bits
     uint32_t threshold;
 };
@@ -133,7 +133,7 @@ __device__ __forceinline__ void tc4_emit(const Tc4Sink &k, uint64_t local_row, u
     } else if (pos < k.cap) {
         YumePDQ_Match m;
         m.row = local_row + k.row_offset;
-        m.needle = needle + k.needle_base;
+        m.needle = k.needle_base(needle);
         m.dist = dist;
         k.out[pos] = m;
     }
