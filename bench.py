@@ -753,11 +753,12 @@ def main():
             e2e["single_frame_abi"] = {
                 "us_per_call": med_pg, "us_per_call_mean": mean_pg,
                 "us_per_call_pinned_input": med_pin, "us_per_call_device_input": med_dev,
-                "path": "yume_pdq_hash_smart_kernel through ctypes, frame in PAGEABLE host memory (median of 300 calls): ONE "
-                        "launch (hash_one_kernel) issued before the copy; the host moves the frame into pinned memory "
-                        "64 KB at a time while the kernel reads the chunks that have arrived over PCIe; results and the "
-                        "completion flag are written to mapped host memory and polled -- no cudaMemcpy, no stream sync.  "
-                        "pinned_input: read in place; device_input: frame already in HBM",
+                "path": "yume_pdq_hash_smart_kernel through ctypes with preallocated buffers, median of 300 calls.  Frame in "
+                        "PAGEABLE host memory: four quarter-frame copies into pinned memory (non-temporal stores), each handed "
+                        "to the copy engine as soon as it is there, then ONE launch (hash_one_kernel: 128 CTAs for the tent "
+                        "rows, the last one to finish runs dct / median / gradients / hash bits); results and the completion "
+                        "flag are written to mapped host memory and polled -- no D2H copy, no stream sync.  pinned_input: one "
+                        "DMA; device_input: frame already in HBM",
                 "reference_published_us": 81.0, "reference_source": "README.md:170-173 (AVX2 build through ctypes, Ryzen 9 7950X)"}
 
     cpu_bl = None
