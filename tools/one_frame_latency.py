@@ -61,3 +61,18 @@ for _ in range(200):
     np.copyto(dst, one)
     ts.append(time.perf_counter() - t0)
 print("host memcpy of 1 MiB into pinned memory: median %.1f us" % (np.median(ts) * 1e6))
+
+# the second function of the reference ABI: 7 callbacks per call
+seen = []
+p0 = o_pdqf.copy()
+thr = float(o_thr.value)
+for _ in range(20):
+    p = p0.copy()
+    yp.visit_dihedrals(p, thr, lambda *a: True)
+ts = []
+for _ in range(300):
+    p = p0.copy()
+    t0 = time.perf_counter()
+    yp.visit_dihedrals(p, thr, lambda *a: True)
+    ts.append(time.perf_counter() - t0)
+print("visit_dihedrals (7 Python callbacks): median %.1f us" % (np.median(ts) * 1e6))

@@ -227,18 +227,6 @@ inline size_t host_bytes(const T *p, size_t bytes)
     return (p && !is_device_ptr(p)) ? align_up(bytes, 256) : 0;
 }
 
-__global__ void dihedral_states_kernel(const float *__restrict__ pdqf, float *__restrict__ states)
-{
-    // states[d-1][i][j], d = 1..7, same sign/transposition table as hasher.cu:dihedral_value
-    const int tid = threadIdx.x, i = tid >> 4, j = tid & 15;
-    for (int d = 1; d < 8; d++) {
-        float v = (d & 4) ? pdqf[j * 16 + i] : pdqf[i * 16 + j];
-        const bool c = (0xC6 >> d) & 1, r = (0x6C >> d) & 1;
-        const bool neg = (c && !(j & 1)) != (r && !(i & 1));
-        states[(d - 1) * 256 + tid] = neg ? -v : v;
-    }
-}
-
 // the single-frame latency path's buffers, per (host thread, device): the tent buffer, the finished-CTA counter and the
 // frame in device memory, results + staging block in pinned (mapped) host memory
 #ifndef YPDQ_ONE_FRAME_PARTS
@@ -278,7 +266,8 @@ struct OneFrameCtx {
     OneFrameOut *out = nullptr;
     float *stage = nullptr;
     float *frame_dev = nullptr;
-    uint32_t seq = 0;
+    VisitOut *visit = nullptr;    // yume_pdq_visit_dihedrals_smart_kernel's results (pinned)
+    uint32_t seq = 0, visit_seq = 0;
     double stamps_us[8] = {0};    // host-side stamps of the last call (diagnostic)
     int init(int device_)
     {
@@ -287,7 +276,7 @@ struct OneFrameCtx {
         device = device_;
         void *d = nullptr, *h = nullptr, *st = nullptr;
         if (cudaMalloc(&d, 128 * 128 * 4 + 256 + 512 * 512 * 4) != cudaSuccess || cudaMemset(d, 0, 128 * 128 * 4 + 256) != cudaSuccess ||
-            cudaMallocHost(&h, sizeof(OneFrameOut)) != cudaSuccess ||
+            cudaMallocHost(&h, sizeof(OneFrameOut) + sizeof(VisitOut)) != cudaSuccess ||
             cudaMallocHost(&st, 512 * 512 * 4) != cudaSuccess) {
             (void)cudaGetLastError();
             if (d)
@@ -296,11 +285,12 @@ struct OneFrameCtx {
                 cudaFreeHost(h);
             return YUME_PDQ_CUDA_E_NOMEM;
         }
-        std::memset(h, 0, sizeof(OneFrameOut));
+        std::memset(h, 0, sizeof(OneFrameOut) + sizeof(VisitOut));
         buf1_dev = static_cast<float *>(d);
         done = reinterpret_cast<unsigned int *>(static_cast<uint8_t *>(d) + 128 * 128 * 4);
         frame_dev = reinterpret_cast<float *>(static_cast<uint8_t *>(d) + 128 * 128 * 4 + 256);
         out = static_cast<OneFrameOut *>(h);
+        visit = reinterpret_cast<VisitOut *>(static_cast<uint8_t *>(h) + sizeof(OneFrameOut));
         stage = static_cast<float *>(st);
         return 0;
     }
@@ -321,6 +311,30 @@ struct OneFrameCtx {
         (void)cudaGetLastError();
     }
 };
+// spin on a sequence number the kernel writes last into mapped host memory (the store is visible ~1 us after it is
+// issued; a stream synchronisation wakes up ~8 us later); falls back to the stream when the kernel has ended without it
+bool poll_seq(volatile unsigned int *flag, uint32_t seq, cudaStream_t s)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    uint32_t spins = 0;
+    while (*flag != seq) {
+        if ((++spins & 0x3FFFu) == 0) {
+            if (cudaStreamQuery(s) != cudaErrorNotReady)      // finished (or failed) without the store becoming visible
+                break;
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5))
+                break;
+        }
+    }
+    if (*flag != seq) {
+        if (cudaStreamSynchronize(s) != cudaSuccess || *flag != seq) {
+            (void)cudaGetLastError();
+            return false;
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return true;
+}
+
 OneFrameCtx &tls_one_frame(int device)
 {
     static thread_local OneFrameCtx c[kMaxDevices];
@@ -442,24 +456,8 @@ float yume_pdq_hash_smart_kernel(const float *input, float *threshold, uint8_t *
     if (launch_hash_one(frame, cx.buf1_dev, cx.done, h, seq, avx2_style, s) != 0)
         return nan;
     stamp(1);
-    volatile unsigned int *flag = &h->seq;
-    const auto t0 = std::chrono::steady_clock::now();
-    uint32_t spins = 0;
-    while (*flag != seq) {
-        if ((++spins & 0x3FFFu) == 0) {
-            if (cudaStreamQuery(s) != cudaErrorNotReady)      // finished (or failed) without the store becoming visible
-                break;
-            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5))
-                break;
-        }
-    }
-    if (*flag != seq) {
-        if (cudaStreamSynchronize(s) != cudaSuccess || *flag != seq) {
-            (void)cudaGetLastError();
-            return nan;
-        }
-    }
-    std::atomic_thread_fence(std::memory_order_acquire);
+    if (!poll_seq(&h->seq, seq, s))
+        return nan;
     stamp(2);
     std::memcpy(buf1, h->buf1, sizeof h->buf1);
     std::memcpy(pdqf, h->pdqf, sizeof h->pdqf);
@@ -491,35 +489,21 @@ bool yume_pdq_visit_dihedrals_smart_kernel(void *ctx, float threshold, uint8_t *
     const int device = default_device();
     if (!output || !pdqf || !callback || ensure_device(device) != 0)
         return false;
-    Scratch &sc = tls_scratch(1, device);
-    if (sc.reserve(device, 16 * 1024, 16 * 1024) != 0)
+    // one launch, no copies: the PDQF travels in the launch parameters, the kernel writes the 7 transformed PDQFs, the
+    // hashes and the qualities into mapped host memory and then a sequence number this thread polls
+    OneFrameCtx &cx = tls_one_frame(device);
+    if (cx.init(device) != 0)
         return false;
-    float *d_p = reinterpret_cast<float *>(sc.dev);
-    float *d_states = d_p + 256;
-    float *d_thr0 = d_states + 7 * 256;
-    float *d_quality = d_thr0 + 64;
-    uint8_t *d_hashes = reinterpret_cast<uint8_t *>(d_quality + 64);
     cudaStream_t s = nullptr;
-    struct HostOut {
-        float states[7 * 256];
-        float quality[8];
-        uint8_t hashes[256];
-    };
-    HostOut *h = reinterpret_cast<HostOut *>(sc.pin);
-    if (cudaMemcpyAsync(d_p, pdqf, 1024, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-        cudaMemcpyAsync(d_thr0, &threshold, 4, cudaMemcpyHostToDevice, s) != cudaSuccess)
+    using HostOut = VisitOut;
+    HostOut *h = cx.visit;
+    VisitIn in;
+    std::memcpy(in.p, pdqf, sizeof in.p);
+    const uint32_t seq = ++cx.visit_seq;
+    if (launch_dihedrals_one(in, threshold, h, seq, s) != 0)
         return false;
-    if (launch_dihedrals(d_p, d_thr0, 1, d_hashes, d_quality, nullptr, s) != 0)
+    if (!poll_seq(&h->seq, seq, s))
         return false;
-    dihedral_states_kernel<<<1, 256, 0, s>>>(d_p, d_states);
-    g_launches.fetch_add(1);
-    if (cudaMemcpyAsync(h->states, d_states, sizeof h->states, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaMemcpyAsync(h->quality, d_quality, sizeof h->quality, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaMemcpyAsync(h->hashes, d_hashes, sizeof h->hashes, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaStreamSynchronize(s) != cudaSuccess) {
-        (void)cudaGetLastError();
-        return false;
-    }
     // lib.rs:381-419: 7 callbacks; lib.rs:223-224: the callback sees the ORIGINAL threshold
     HostOut local = *h;  // the callback may re-enter this library on the same thread
     for (int d = 1; d < 8; d++) {

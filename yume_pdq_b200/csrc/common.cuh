@@ -255,6 +255,17 @@ struct OneFrameOut {                      // mapped host memory, written by the 
     long long trace[8];                   // diagnostic, SM clocks of the finishing CTA: start, elected, tent buffer staged,
                                           // dct stage 1, stage 2, median + gradients, hash bits
 };
+struct VisitIn {                          // the PDQF by value in the launch parameters: no upload
+    float p[256];
+};
+struct VisitOut {                         // mapped host memory, written by the kernel
+    float states[7 * 256];                // PDQF of dihedrals 1 .. 7
+    float quality[8];
+    uint8_t hashes[8 * 32];
+    unsigned int seq;                     // written last
+    unsigned int pad[7];
+};
+int launch_dihedrals_one(const VisitIn &in, float thr0, VisitOut *out, uint32_t seq, cudaStream_t s);
 int launch_hash_one(const float *frame, float *buf1_dev, unsigned int *done, OneFrameOut *out, uint32_t seq, bool avx2_style,
                     cudaStream_t s);
 

@@ -1,8 +1,13 @@
 // hasher.cu -- batched PDQ-variant hasher for sm_100a.
 //
 // One CTA of 128 threads hashes one 512x512 f32 frame in a single pass over the
-// frame and emits all 8 dihedral hashes.  It reproduces the reference scalar
-// kernel (DefaultKernel, /root/reference src/kernel/mod.rs) BIT FOR BIT:
+// frame and emits all 8 dihedral hashes.  The arithmetic is the reference scalar
+// kernel's (DefaultKernel, /root/reference src/kernel/mod.rs), operation by operation, for finite
+// input; two conventions are NOT the scalar kernel's and are listed in DESIGN.md section 5: the
+// dihedral sign flips follow the AVX2 kernel (pdqf_negate_alt_rows::<true> negates EVEN rows,
+// x86.rs:285-326; the scalar trait default negates odd rows, mod.rs:392-405, so only NORMAL and
+// FLOPPED agree with DefaultKernel bit for bit), and the zero / ~1e-40 border taps of the 7x7 tent
+// LUT are not multiplied in (a NaN or Inf pixel in the border ring propagates in the reference only):
 //   jarosz_compress   mod.rs:644-666   tent 7x7 (5x5 effective), di outer / dj inner,
 //                                      separate f32 multiply and add (no FMA)
 //   dct2d             mod.rs:543-574   D(16x127) B D^T with 4 round-robin partial
@@ -859,7 +864,36 @@ hash_one_kernel(const float *__restrict__ frame, float *buf1_dev, unsigned int *
         st_release_sys(&out->seq, seq);
 }
 
+// visit_dihedrals (lib.rs:358-420) for ONE PDQF as a latency path: the PDQF arrives in the launch parameters, the 7
+// transformed PDQFs, 8 hashes and 8 qualities go straight to mapped host memory, then the sequence number
+__global__ void __launch_bounds__(HT)
+dihedrals_one_kernel(const __grid_constant__ VisitIn in, float thr0, VisitOut *out, uint32_t seq)
+{
+    __shared__ HashSmem sm;
+    const int tid = threadIdx.x;
+    sm.p[tid] = in.p[tid];
+    sm.p[128 + tid] = in.p[128 + tid];
+    __syncthreads();
+#pragma unroll 1
+    for (int d = 1; d < 8; d++) {
+        out->states[(d - 1) * 256 + tid] = dihedral_value(sm.p, d, tid >> 4, tid & 15);
+        out->states[(d - 1) * 256 + 128 + tid] = dihedral_value(sm.p, d, (128 + tid) >> 4, tid & 15);
+    }
+    dihedral_epilogue(sm, tid, out->hashes, out->quality, nullptr, true, thr0);
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0)
+        st_release_sys(&out->seq, seq);
+}
+
 }  // namespace
+
+int launch_dihedrals_one(const VisitIn &in, float thr0, VisitOut *out, uint32_t seq, cudaStream_t s)
+{
+    dihedrals_one_kernel<<<1, HT, 0, s>>>(in, thr0, out, seq);
+    YPDQ_LAUNCH_CHECK();
+    return 0;
+}
 
 int launch_hash_batch(const void *frames, int pixel_format, size_t n, uint8_t *hashes, float *quality,
                       float *thresholds, float *pdqf, cudaStream_t s)
