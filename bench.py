@@ -274,6 +274,8 @@ def main():
     ap.add_argument("--no-config4", action="store_true")
     ap.add_argument("--no-worst-case", action="store_true", help="skip the clustered-haystack leg")
     ap.add_argument("--no-config5", action="store_true")
+    ap.add_argument("--nccl-gather", action="store_true",
+                    help="N > 1: all-gather the needles with NCCL instead of the copy-engine exchange over peer memory")
     ap.add_argument("--frames", type=int, default=FRAMES_PER_GPU, help=argparse.SUPPRESS)
     ap.add_argument("--db-rows", type=int, default=DB_ROWS, help=argparse.SUPPRESS)
     ap.add_argument("--c5-rows-per-gpu", type=int, default=125_000_000, help=argparse.SUPPRESS)
@@ -345,6 +347,9 @@ def main():
     side = torch.cuda.Stream(dev) if n_gpus > 1 else None
     ev_hash, ev_gath, ev_match, ev_list = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
     others = torch.empty((q_all - q_loc, 32), dtype=torch.uint8, device=dev) if n_gpus > 1 else None
+    exchange = None
+    if n_gpus > 1 and not args.nccl_gather:
+        exchange = sharded.make_exchange(local_rank, rank, n_gpus, q_loc * 32)
 
     # plant rows so the scan has something to find: copies of this job's own hashes, 0..31 bits away
     kern.hash_batch(frames, out=outs)
@@ -361,34 +366,64 @@ def main():
         db.write_rows(lrow, np.packbits(h)[None])
         planted.append((row0 + lrow, rank * q_loc + j))
 
-    def step():
+    def step(tl=None):
+        # tl: optional dict of timing events (the untimed timeline pass after the timed region)
+        def mark(name, stream=None):
+            if tl is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record(stream or main_stream)
+                tl[name] = e
+        mark("start")
         kern.hash_batch(frames, out=outs)
+        mark("hashed")
         if n_gpus == 1:
             match_cnt.zero_()
             matcher.find_device(local_needles, q_loc, match_out, CAP, match_cnt, algo=yp.ALGO_AUTO)
             return
-        # N > 1: the all-gather of the needles runs on a side stream while this rank's OWN needles are matched; the side
-        # stream then packs the other ranks' needles (everything below and above this rank's slice) into one contiguous
-        # batch that ONE launch matches (find_device_split reports the needle indices of the un-packed list); the
-        # all-gather of {count, match list} runs on the side stream as well, under the next step's hash kernel
+        # N > 1: the all-gather of the needles runs on a side stream while this rank's OWN needles are matched; the other
+        # ranks' needles (everything below and above this rank's slice) then form one contiguous batch that ONE launch
+        # matches (find_device_split reports the needle indices of the un-packed list); the all-gather of {count, match
+        # list} runs on the side stream as well, under the next step's hash kernel.  The needle all-gather is the
+        # copy-engine exchange over peer memory (default) or, with --nccl-gather, NCCL's + two packing copies
         ev_hash.record(main_stream)
-        with torch.cuda.stream(side):
-            side.wait_event(ev_hash)
-            dist.all_gather_into_tensor(needles_all, local_needles)
-            if rank > 0:
-                others[: rank * q_loc].copy_(needles_all[: rank * q_loc], non_blocking=True)
-            if rank < n_gpus - 1:
-                others[rank * q_loc:].copy_(needles_all[(rank + 1) * q_loc:], non_blocking=True)
-            ev_gath.record(side)
-        main_stream.wait_event(ev_list)      # the previous step's list has been gathered before the counter is reset
-        match_cnt.zero_()
-        matcher.find_device(local_needles, q_loc, match_out, CAP, match_cnt, needle_base=rank * q_loc)
-        main_stream.wait_event(ev_gath)
-        matcher.find_device(others, q_all - q_loc, match_out, CAP, match_cnt, split_at=rank * q_loc, gap=q_loc)
+        if exchange is not None:
+            # copy-engine all-gather over peer memory (yume_pdq_cuda_exchange_*): no kernel beside the persistent matcher
+            with torch.cuda.stream(side):
+                side.wait_event(ev_hash)
+                exchange.post(local_needles, stream=side)
+                mark("gathered", side)
+                mark("packed", side)
+                ev_gath.record(side)      # this rank's slice has left: the next hash may overwrite it
+            main_stream.wait_event(ev_list)
+            match_cnt.zero_()
+            matcher.find_device(local_needles, q_loc, match_out, CAP, match_cnt, needle_base=rank * q_loc)
+            mark("own_matched")
+            main_stream.wait_event(ev_gath)
+            others_ptr = exchange.wait(stream=main_stream)      # one-warp kernel: every peer's slice is in
+            matcher.find_device(others_ptr, q_all - q_loc, match_out, CAP, match_cnt, split_at=rank * q_loc, gap=q_loc)
+        else:
+            with torch.cuda.stream(side):
+                side.wait_event(ev_hash)
+                dist.all_gather_into_tensor(needles_all, local_needles)
+                mark("gathered", side)
+                if rank > 0:
+                    others[: rank * q_loc].copy_(needles_all[: rank * q_loc], non_blocking=True)
+                if rank < n_gpus - 1:
+                    others[rank * q_loc:].copy_(needles_all[(rank + 1) * q_loc:], non_blocking=True)
+                mark("packed", side)
+                ev_gath.record(side)
+            main_stream.wait_event(ev_list)      # the previous step's list has been gathered before the counter is reset
+            match_cnt.zero_()
+            matcher.find_device(local_needles, q_loc, match_out, CAP, match_cnt, needle_base=rank * q_loc)
+            mark("own_matched")
+            main_stream.wait_event(ev_gath)
+            matcher.find_device(others, q_all - q_loc, match_out, CAP, match_cnt, split_at=rank * q_loc, gap=q_loc)
+        mark("others_matched")
         ev_match.record(main_stream)
         with torch.cuda.stream(side):
             side.wait_event(ev_match)
             dist.all_gather_into_tensor(gathered.reshape(-1, 16), list_buf)
+            mark("lists_gathered", side)
             ev_list.record(side)
 
     for _ in range(args.warmup):
@@ -418,6 +453,22 @@ def main():
     elapsed_ms = max_over_ranks(elapsed_ms)
     ms_per_step = elapsed_ms / args.steps
     value = n_gpus * B / (ms_per_step * 1e-3)
+
+    # ---- untimed: where a step's time goes (CUDA events inside four more steps; ms after the step's start, median) ----
+    timeline = None
+    if n_gpus > 1:
+        tls = [dict() for _ in range(5)]
+        for tl in tls:
+            step(tl)
+        torch.cuda.synchronize()
+        names = ["hashed", "gathered", "packed", "own_matched", "others_matched", "lists_gathered"]
+        mine = {n: float(np.median([tl["start"].elapsed_time(tl[n]) for tl in tls[1:]])) for n in names}
+        mine["next_start"] = float(np.median([tls[i]["start"].elapsed_time(tls[i + 1]["start"]) for i in range(1, 4)]))
+        timeline = {"rank0_ms": mine, "max_over_ranks_ms": {n: max_over_ranks(v) for n, v in mine.items()},
+                    "note": "main stream: hashed -> own_matched -> others_matched; side stream: gathered (NCCL all-gather of "
+                            "the needles) -> packed (two D2D copies) and lists_gathered (NCCL all-gather of count + list, "
+                            "under the next step's hash)"}
+        barrier()
 
     # ---- correctness of what was timed (untimed check) -----------------------
     n_matches = int(match_cnt.item())
@@ -774,7 +825,10 @@ def main():
             "e2e": e2e, "gpu_launches": int(lt.item()), "clocks": clocks,
             "matches_per_step": total_matches, "planted": N_PLANT * n_gpus,
             "parity_checked": bool(parity and parity.get("checked")), "parity": parity,
-            "config5": c5, "config4": c4, "worst_case": worst,
+            "config5": c5, "config4": c4, "worst_case": worst, "step_timeline": timeline,
+            "needle_gather": None if n_gpus == 1 else
+            ("NCCL all-gather + two packing copies" if exchange is None else
+             "copy-engine pushes over peer memory (yume_pdq_cuda_exchange_*: CUDA IPC buffers, flag words, no kernel)"),
             "cpu_baseline": cpu_bl,
         }
         line.update(line_extra)

@@ -210,6 +210,27 @@ int yume_pdq_cuda_mailbox_set_mode(YumePDQ_CudaMailbox *mb, int mode);
  * launches; answer in) */
 int yume_pdq_cuda_mailbox_last_timing(const YumePDQ_CudaMailbox *mb, double *out5);
 
+/* ---- needle all-gather over peer memory with the copy engines (one process per GPU, no kernel on the data path) ----
+ * Every rank pushes its slice (slice_bytes, the same on every rank) into a buffer in every peer's HBM (CUDA IPC, copy-engine
+ * copies over NVLink) followed, in stream order, by a sequence number in the peer's flag word; `wait` makes a stream wait
+ * (one-warp kernel) until every peer's slice of the latest `post` is in and returns this rank's buffer: the world - 1
+ * slices of the OTHER ranks in rank order -- the packed batch yume_pdq_cuda_matcher_find_device_split takes with
+ * split_at = rank * needles_per_slice and gap = needles_per_slice.  Unlike an NCCL all-gather it needs no SM, so it does
+ * not delay a persistent matcher kernel running beside it.
+ *   create / connect : as for the mailboxes (handle_out: YUME_PDQ_CUDA_IPC_HANDLE_BYTES; handles rank-ordered)
+ *   post   : COLLECTIVE, enqueues on `stream`; slice_dev must stay unchanged until the stream has passed this point
+ *   wait   : enqueues on `stream`; *others_dev is valid until the post after next (two buffers alternate).  The caller
+ *            must keep ranks within one exchange of each other (a per-step collective such as the match-list gather does)
+ *   failed : (synchronises) nonzero if a wait gave up after 2 s */
+typedef struct YumePDQ_CudaExchange YumePDQ_CudaExchange;
+int yume_pdq_cuda_exchange_create(int device, int rank, int world, size_t slice_bytes, YumePDQ_CudaExchange **out,
+                                  uint8_t *handle_out);
+int yume_pdq_cuda_exchange_connect(YumePDQ_CudaExchange *ex, const uint8_t *handles);
+int yume_pdq_cuda_exchange_post(YumePDQ_CudaExchange *ex, const void *slice_dev, void *stream);
+int yume_pdq_cuda_exchange_wait(YumePDQ_CudaExchange *ex, void *stream, const uint8_t **others_dev);
+int yume_pdq_cuda_exchange_failed(YumePDQ_CudaExchange *ex, int *failed);
+int yume_pdq_cuda_exchange_destroy(YumePDQ_CudaExchange *ex);
+
 /* Kernel selection for the matcher (0 = automatic) */
 #define YUME_PDQ_CUDA_ALGO_AUTO 0
 #define YUME_PDQ_CUDA_ALGO_EXACT 1   /* unfiltered: 8 POPC per (row, needle) pair */

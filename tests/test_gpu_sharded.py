@@ -201,3 +201,78 @@ def test_two_gpu_fused_mailbox_query(tmp_path, oracle):
     world = 2
     mp.spawn(_fused_worker, args=(world, _free_port(), 2_200_006, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"fused_ok{r}.npy") for r in range(world))
+
+
+def _exchange_worker(rank, world, port, result_dir):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    for p in (here, os.path.dirname(here)):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+
+    import yume_pdq_b200 as yp
+    from oracle import pyoracle
+    from yume_pdq_b200 import sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    orc = pyoracle.get()
+    q_loc = 1024
+    ex = sharded.make_exchange(rank, rank, world, q_loc * 32)
+    n_rows = 300_000
+    rows = orc.synth_db(n_rows, first_row=9)
+    per = n_rows // world
+    db = yp.CudaVectorDatabase(rows[rank * per:(rank + 1) * per if rank < world - 1 else n_rows], device=rank,
+                               global_row_offset=rank * per)
+    m = yp.CudaMatcher(db, 31)
+    side = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    out = torch.zeros((1 << 12, 16), dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    mine = torch.empty((q_loc, 32), dtype=torch.uint8, device="cuda")
+    ev = torch.cuda.Event()
+    for step in range(12):
+        # every rank derives every rank's needles of this step; plants make some of them match rows of either shard
+        rr = np.random.default_rng(1000 + step)
+        needles_all = rr.integers(0, 256, size=(world * q_loc, 32), dtype=np.uint8)
+        for k in range(40):
+            needles_all[int(rr.integers(0, world * q_loc))] = flip_bits(rows[int(rr.integers(0, n_rows))], int(rr.integers(0, 32)), rr)
+        main.wait_event(ev)                      # the previous push of `mine` is done
+        mine.copy_(torch.from_numpy(needles_all[rank * q_loc:(rank + 1) * q_loc]))
+        done = torch.cuda.Event()
+        done.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(done)
+            ex.post(mine, stream=side)
+            ev.record(side)
+        cnt.zero_()
+        m.find_device(mine, q_loc, out, 1 << 12, cnt, needle_base=rank * q_loc)
+        others = ex.wait(stream=main)
+        m.find_device(others, (world - 1) * q_loc, out, 1 << 12, cnt, split_at=rank * q_loc, gap=q_loc)
+        torch.cuda.synchronize()
+        got = sorted(match_tuples(out[: int(cnt.item())].cpu().numpy().view(yp.MATCH_DTYPE).reshape(-1)))
+        lo, hi = rank * per, ((rank + 1) * per if rank < world - 1 else n_rows)
+        want = sorted(t for t in match_tuples(orc.matcher_find(rows, needles_all, 31)) if lo <= t[0] < hi)
+        assert got == want, (step, len(got), len(want))
+        assert len(want) > 5
+        dist.barrier()                           # ranks stay within one exchange of each other
+    assert not ex.failed()
+    ex.close()
+    db.close()
+    np.save(os.path.join(result_dir, f"ex_ok{rank}.npy"), np.array([1]))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_peer_exchange(tmp_path, oracle):
+    """The copy-engine needle all-gather (yume_pdq_cuda_exchange_*) + find_device_split: twelve steps with fresh needles,
+    every rank's match list must be the oracle's for its shard with the un-packed needle indices."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    world = 2
+    mp.spawn(_exchange_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"ex_ok{r}.npy") for r in range(world))

@@ -104,6 +104,12 @@ SIGNATURES = {
     "yume_pdq_cuda_mailbox_destroy": (C.c_int, [_vp]),
     "yume_pdq_cuda_mailbox_last_timing": (C.c_int, [_vp, C.POINTER(C.c_double)]),
     "yume_pdq_cuda_mailbox_set_mode": (C.c_int, [_vp, C.c_int]),
+    "yume_pdq_cuda_exchange_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(_vp), _vp]),
+    "yume_pdq_cuda_exchange_connect": (C.c_int, [_vp, C.c_char_p]),
+    "yume_pdq_cuda_exchange_post": (C.c_int, [_vp, _vp, _vp]),
+    "yume_pdq_cuda_exchange_wait": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "yume_pdq_cuda_exchange_failed": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "yume_pdq_cuda_exchange_destroy": (C.c_int, [_vp]),
     "yume_pdq_cuda_one_frame_last_timing": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "yume_pdq_cuda_mailbox_scan": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_uint32, C.c_int, C.POINTER(C.c_uint32), _vp]),
     "yume_pdq_cuda_db_auto_state": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_uint32)]),
@@ -636,6 +642,49 @@ class PeerMailbox:
     def close(self):
         if self._h:
             lib.yume_pdq_cuda_mailbox_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PeerExchange:
+    """This rank's end of the copy-engine needle all-gather (yume_pdq_cuda_exchange_*): `handle` goes to the peers,
+    `connect` takes everyone's handles in rank order; `post(slice)` pushes this rank's slice to every peer, `wait()`
+    makes a stream wait for the peers' slices and returns the device address of the packed batch of the other ranks'
+    slices (rank order).  yume_pdq_b200.sharded.make_exchange wires it to torch.distributed."""
+
+    def __init__(self, device: int, rank: int, world: int, slice_bytes: int):
+        self._h = _vp()
+        buf = (C.c_uint8 * IPC_HANDLE_BYTES)()
+        _check(lib.yume_pdq_cuda_exchange_create(device, rank, world, slice_bytes, C.byref(self._h), buf), "exchange_create")
+        self.handle = bytes(buf)
+        self.rank, self.world, self.slice_bytes = rank, world, slice_bytes
+
+    def connect(self, handles):
+        blob = b"".join(handles)
+        assert len(blob) == self.world * IPC_HANDLE_BYTES
+        _check(lib.yume_pdq_cuda_exchange_connect(self._h, C.c_char_p(blob)), "exchange_connect")
+
+    def post(self, slice_dev, stream=None):
+        _check(lib.yume_pdq_cuda_exchange_post(self._h, _ptr(slice_dev), _stream(stream)), "exchange_post")
+
+    def wait(self, stream=None) -> int:
+        p = _vp()
+        _check(lib.yume_pdq_cuda_exchange_wait(self._h, _stream(stream), C.byref(p)), "exchange_wait")
+        return int(p.value or 0)
+
+    def failed(self) -> bool:
+        f = C.c_int(0)
+        _check(lib.yume_pdq_cuda_exchange_failed(self._h, C.byref(f)), "exchange_failed")
+        return bool(f.value)
+
+    def close(self):
+        if self._h:
+            lib.yume_pdq_cuda_exchange_destroy(self._h)
             self._h = _vp()
 
     def __del__(self):

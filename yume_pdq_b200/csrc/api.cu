@@ -1585,3 +1585,200 @@ int yume_pdq_cuda_mailbox_last_timing(const YumePDQ_CudaMailbox *mb, double *out
 }
 
 }  // extern "C"
+
+// ----------------------------------------------------------------------------------------------------------------
+// Peer exchange: the all-gather of every rank's needle slice WITHOUT a kernel.  NCCL's all-gather is a kernel: issued
+// beside the persistent tensor matcher it takes SMs first, the matcher's CTAs on those SMs start late and the whole
+// launch ends late by the all-gather's duration (measured on 4 B200s, bench.py step_timeline: 0.157 ms of all-gather
+// -> own-needle match 2.885 ms instead of 2.736).  Here every rank owns a buffer that the others map through CUDA IPC
+// and PUSHES its slice into every peer's buffer with copy-engine copies over NVLink, each followed, in stream order, by
+// a 4-byte copy of the sequence number into the peer's flag word for this rank; the consumer's stream waits for the
+// world - 1 flags with a one-warp kernel right before the launch that needs the data.  A rank's slice lands at its
+// position among the OTHER ranks' slices, so the buffer is the packed batch yume_pdq_cuda_matcher_find_device_split
+// takes.  Two buffers alternate by sequence number: a peer may be one exchange ahead (the caller's per-step
+// synchronisation -- the match-list gather in ShardedMatcher / bench.py -- keeps it from being two ahead).
+namespace ypdq {
+namespace {
+
+constexpr int kExchangeRing = 65536;      // ring[i] = i: the source words of the flag copies (16-bit sequence numbers)
+
+struct ExchangeFlags {
+    unsigned int from[kMailboxMaxWorld];  // from[r]: sequence number of the last slice rank r has pushed here
+    unsigned int error;
+    unsigned int pad[15];
+};
+
+__global__ void exchange_ring_kernel(unsigned int *ring)
+{
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (unsigned)kExchangeRing)
+        ring[i] = i;
+}
+
+__global__ void __launch_bounds__(32)
+exchange_wait_kernel(ExchangeFlags *flags, int world, int rank, uint32_t want)
+{
+    const int r = threadIdx.x;
+    if (r < world && r != rank) {
+        const unsigned long long t0 = global_ns();
+        // 16-bit sequence numbers: "at or past `want`" is a signed distance
+        while ((int16_t)(uint16_t)(ld_acquire_sys(&flags->from[r]) - want) < 0) {
+            if (global_ns() - t0 > kMailboxTimeoutNs) {
+                flags->error = 1;
+                break;
+            }
+        }
+    }
+}
+
+}  // namespace
+}  // namespace ypdq
+
+struct YumePDQ_CudaExchange {
+    int device = 0, rank = 0, world = 1;
+    size_t slice_bytes = 0, buf_bytes = 0;      // buf_bytes = (world - 1) * slice_bytes, 256-byte aligned
+    uint32_t seq = 0;
+    uint8_t *mine = nullptr;                    // [buf 0][buf 1][ExchangeFlags]
+    uint8_t *peer[ypdq::kMailboxMaxWorld] = {nullptr};
+    unsigned int *ring = nullptr;               // local
+    bool connected = false;
+    ypdq::ExchangeFlags *flags_of(uint8_t *base) const { return reinterpret_cast<ypdq::ExchangeFlags *>(base + 2 * buf_bytes); }
+};
+
+extern "C" {
+
+int yume_pdq_cuda_exchange_create(int device, int rank, int world, size_t slice_bytes, YumePDQ_CudaExchange **out,
+                                  uint8_t *handle_out)
+{
+    using namespace ypdq;
+    if (!out || !handle_out || world < 1 || world > kMailboxMaxWorld || rank < 0 || rank >= world || slice_bytes == 0 ||
+        slice_bytes % 16 != 0)
+        return YUME_PDQ_CUDA_E_INVALID;
+    int rc = ensure_device(device);
+    if (rc)
+        return rc;
+    auto *ex = new (std::nothrow) YumePDQ_CudaExchange();
+    if (!ex)
+        return YUME_PDQ_CUDA_E_NOMEM;
+    ex->device = device;
+    ex->rank = rank;
+    ex->world = world;
+    ex->slice_bytes = slice_bytes;
+    ex->buf_bytes = align_up((size_t)std::max(1, world - 1) * slice_bytes, 256);
+    const size_t total = 2 * ex->buf_bytes + sizeof(ExchangeFlags);
+    cudaError_t e = cudaMalloc(&ex->mine, total);
+    if (e == cudaSuccess)
+        e = cudaMemset(ex->mine + 2 * ex->buf_bytes, 0, sizeof(ExchangeFlags));
+    if (e == cudaSuccess)
+        e = cudaMalloc(&ex->ring, kExchangeRing * sizeof(unsigned int));
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) {
+        exchange_ring_kernel<<<kExchangeRing / 256, 256>>>(ex->ring);
+        e = cudaDeviceSynchronize();
+    }
+    if (e == cudaSuccess)
+        e = cudaIpcGetMemHandle(&h, ex->mine);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        yume_pdq_cuda_exchange_destroy(ex);
+        return e == cudaErrorMemoryAllocation ? YUME_PDQ_CUDA_E_NOMEM : (int)e;
+    }
+    std::memcpy(handle_out, &h, sizeof(h));
+    ex->peer[rank] = ex->mine;
+    *out = ex;
+    return 0;
+}
+
+int yume_pdq_cuda_exchange_connect(YumePDQ_CudaExchange *ex, const uint8_t *handles)
+{
+    if (!ex || !handles || ex->connected)
+        return YUME_PDQ_CUDA_E_INVALID;
+    int rc = ypdq::ensure_device(ex->device);
+    if (rc)
+        return rc;
+    for (int r = 0; r < ex->world; r++) {
+        if (r == ex->rank)
+            continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + (size_t)r * sizeof(h), sizeof(h));
+        void *p = nullptr;
+        YPDQ_CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ex->peer[r] = static_cast<uint8_t *>(p);
+    }
+    ex->connected = true;
+    return 0;
+}
+
+int yume_pdq_cuda_exchange_post(YumePDQ_CudaExchange *ex, const void *slice_dev, void *stream)
+{
+    using namespace ypdq;
+    if (!ex || !ex->connected || !slice_dev)
+        return YUME_PDQ_CUDA_E_INVALID;
+    int rc = ensure_device(ex->device);
+    if (rc)
+        return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t seq = ++ex->seq;
+    const size_t buf = (seq & 1u) * ex->buf_bytes;
+    // rank r's slice is slot (r < p ? r : r - 1) of peer p's buffer: p's buffer holds every slice but p's own, in rank order
+    for (int d = 1; d < ex->world; d++) {
+        const int p = (ex->rank + d) % ex->world;      // start with the next rank: the pushes of all ranks fan out evenly
+        const size_t slot = (size_t)(ex->rank < p ? ex->rank : ex->rank - 1);
+        YPDQ_CUDA_TRY(cudaMemcpyAsync(ex->peer[p] + buf + slot * ex->slice_bytes, slice_dev, ex->slice_bytes, cudaMemcpyDeviceToDevice, s));
+    }
+    for (int d = 1; d < ex->world; d++) {
+        const int p = (ex->rank + d) % ex->world;
+        YPDQ_CUDA_TRY(cudaMemcpyAsync(&ex->flags_of(ex->peer[p])->from[ex->rank], ex->ring + (seq & (kExchangeRing - 1)), 4,
+                                      cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+}
+
+int yume_pdq_cuda_exchange_wait(YumePDQ_CudaExchange *ex, void *stream, const uint8_t **others_dev)
+{
+    using namespace ypdq;
+    if (!ex || !ex->connected || !others_dev || ex->seq == 0)
+        return YUME_PDQ_CUDA_E_INVALID;
+    int rc = ensure_device(ex->device);
+    if (rc)
+        return rc;
+    *others_dev = ex->mine + (ex->seq & 1u) * ex->buf_bytes;
+    if (ex->world > 1) {
+        exchange_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ex->flags_of(ex->mine), ex->world, ex->rank,
+                                                               ex->seq & (kExchangeRing - 1));
+        YPDQ_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+int yume_pdq_cuda_exchange_failed(YumePDQ_CudaExchange *ex, int *failed)
+{
+    if (!ex || !failed)
+        return YUME_PDQ_CUDA_E_INVALID;
+    int rc = ypdq::ensure_device(ex->device);
+    if (rc)
+        return rc;
+    unsigned int err = 0;
+    YPDQ_CUDA_TRY(cudaMemcpy(&err, &ex->flags_of(ex->mine)->error, 4, cudaMemcpyDeviceToHost));
+    *failed = err != 0;
+    return 0;
+}
+
+int yume_pdq_cuda_exchange_destroy(YumePDQ_CudaExchange *ex)
+{
+    if (!ex)
+        return 0;
+    (void)cudaSetDevice(ex->device);
+    for (int r = 0; r < ex->world; r++)
+        if (r != ex->rank && ex->peer[r])
+            (void)cudaIpcCloseMemHandle(ex->peer[r]);
+    if (ex->mine)
+        cudaFree(ex->mine);
+    if (ex->ring)
+        cudaFree(ex->ring);
+    (void)cudaGetLastError();
+    delete ex;
+    return 0;
+}
+
+}  // extern "C"

@@ -31,6 +31,19 @@ def shard_range(n_rows: int, rank: int, world: int) -> tuple[int, int]:
     return begin, end
 
 
+def make_exchange(device: int, rank: int, world: int, slice_bytes: int, group=None):
+    """A connected PeerExchange (the copy-engine all-gather of every rank's needle slice): allocates this rank's
+    buffers, all-gathers the 64-byte CUDA IPC handles over torch.distributed and maps the peers'.  COLLECTIVE."""
+    import torch.distributed as dist
+    from . import PeerExchange
+    ex = PeerExchange(device, rank, world, slice_bytes)
+    handles = [None] * world
+    dist.all_gather_object(handles, ex.handle, group=group)
+    ex.connect(handles)
+    dist.barrier(group=group)
+    return ex
+
+
 def needle_base(rank: int, images_per_rank: int, dihedrals: int = 8) -> int:
     """Index of rank's first needle in the all-gathered needle array."""
     return rank * images_per_rank * dihedrals
