@@ -347,9 +347,10 @@ def main():
     side = torch.cuda.Stream(dev) if n_gpus > 1 else None
     ev_hash, ev_gath, ev_match, ev_list = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
     others = torch.empty((q_all - q_loc, 32), dtype=torch.uint8, device=dev) if n_gpus > 1 else None
-    exchange = None
+    exchange = exchange_lists = None
     if n_gpus > 1 and not args.nccl_gather:
         exchange = sharded.make_exchange(local_rank, rank, n_gpus, q_loc * 32)
+        exchange_lists = sharded.make_exchange(local_rank, rank, n_gpus, (1 + CAP) * 16)
 
     # plant rows so the scan has something to find: copies of this job's own hashes, 0..31 bits away
     kern.hash_batch(frames, out=outs)
@@ -380,44 +381,45 @@ def main():
             match_cnt.zero_()
             matcher.find_device(local_needles, q_loc, match_out, CAP, match_cnt, algo=yp.ALGO_AUTO)
             return
-        # N > 1: the all-gather of the needles runs on a side stream while this rank's OWN needles are matched; the other
-        # ranks' needles (everything below and above this rank's slice) then form one contiguous batch that ONE launch
-        # matches (find_device_split reports the needle indices of the un-packed list); the all-gather of {count, match
-        # list} runs on the side stream as well, under the next step's hash kernel.  The needle all-gather is the
-        # copy-engine exchange over peer memory (default) or, with --nccl-gather, NCCL's + two packing copies
-        ev_hash.record(main_stream)
+        # N > 1.  Default: NO collective library inside the step -- the needles and the {count, match list} blocks travel
+        # through the peer exchange (yume_pdq_cuda_exchange_*: one push kernel stores a rank's block into every peer's HBM
+        # over NVLink, flag words order it, a one-warp kernel waits), everything on ONE stream:
+        #   hash -> push needles -> match OWN needles -> wait for the peers' needles -> match them in ONE launch
+        #   (find_device_split: the packed batch of the other ranks, indices of the un-packed list) -> push the list block;
+        # the peers' list blocks of step i are waited for at the end of the timed region / by whoever consumes them.
+        # --nccl-gather: the NCCL formulation (needle all-gather + two packing copies on a side stream beside the own-needle
+        # match, list all-gather under the next hash); measured slower because NCCL's kernels share the SMs with the
+        # persistent matcher and with the hash kernel (step_timeline)
         if exchange is not None:
-            # copy-engine all-gather over peer memory (yume_pdq_cuda_exchange_*): no kernel beside the persistent matcher
-            with torch.cuda.stream(side):
-                side.wait_event(ev_hash)
-                exchange.post(local_needles, stream=side)
-                mark("gathered", side)
-                mark("packed", side)
-                ev_gath.record(side)      # this rank's slice has left: the next hash may overwrite it
-            main_stream.wait_event(ev_list)
+            exchange.post(local_needles, stream=main_stream)
+            mark("gathered")
+            mark("packed")
             match_cnt.zero_()
             matcher.find_device(local_needles, q_loc, match_out, CAP, match_cnt, needle_base=rank * q_loc)
             mark("own_matched")
-            main_stream.wait_event(ev_gath)
             others_ptr = exchange.wait(stream=main_stream)      # one-warp kernel: every peer's slice is in
             matcher.find_device(others_ptr, q_all - q_loc, match_out, CAP, match_cnt, split_at=rank * q_loc, gap=q_loc)
-        else:
-            with torch.cuda.stream(side):
-                side.wait_event(ev_hash)
-                dist.all_gather_into_tensor(needles_all, local_needles)
-                mark("gathered", side)
-                if rank > 0:
-                    others[: rank * q_loc].copy_(needles_all[: rank * q_loc], non_blocking=True)
-                if rank < n_gpus - 1:
-                    others[rank * q_loc:].copy_(needles_all[(rank + 1) * q_loc:], non_blocking=True)
-                mark("packed", side)
-                ev_gath.record(side)
-            main_stream.wait_event(ev_list)      # the previous step's list has been gathered before the counter is reset
-            match_cnt.zero_()
-            matcher.find_device(local_needles, q_loc, match_out, CAP, match_cnt, needle_base=rank * q_loc)
-            mark("own_matched")
-            main_stream.wait_event(ev_gath)
-            matcher.find_device(others, q_all - q_loc, match_out, CAP, match_cnt, split_at=rank * q_loc, gap=q_loc)
+            mark("others_matched")
+            exchange_lists.post(list_buf, stream=main_stream)
+            mark("lists_gathered")
+            return
+        ev_hash.record(main_stream)
+        with torch.cuda.stream(side):
+            side.wait_event(ev_hash)
+            dist.all_gather_into_tensor(needles_all, local_needles)
+            mark("gathered", side)
+            if rank > 0:
+                others[: rank * q_loc].copy_(needles_all[: rank * q_loc], non_blocking=True)
+            if rank < n_gpus - 1:
+                others[rank * q_loc:].copy_(needles_all[(rank + 1) * q_loc:], non_blocking=True)
+            mark("packed", side)
+            ev_gath.record(side)
+        main_stream.wait_event(ev_list)      # the previous step's list has been gathered before the counter is reset
+        match_cnt.zero_()
+        matcher.find_device(local_needles, q_loc, match_out, CAP, match_cnt, needle_base=rank * q_loc)
+        mark("own_matched")
+        main_stream.wait_event(ev_gath)
+        matcher.find_device(others, q_all - q_loc, match_out, CAP, match_cnt, split_at=rank * q_loc, gap=q_loc)
         mark("others_matched")
         ev_match.record(main_stream)
         with torch.cuda.stream(side):
@@ -425,6 +427,47 @@ def main():
             dist.all_gather_into_tensor(gathered.reshape(-1, 16), list_buf)
             mark("lists_gathered", side)
             ev_list.record(side)
+
+    def finish_lists():
+        """The last step's match lists are on every rank (inside the timed region); exchange: copy them into `gathered`."""
+        if n_gpus == 1:
+            return
+        if exchange is None:
+            main_stream.wait_event(ev_list)
+            return
+        exchange_lists.wait(stream=main_stream)
+
+    def collect_lists():
+        """untimed: the exchange's buffer (the other ranks' blocks, rank order) + this rank's own block -> `gathered`"""
+        if exchange is None:
+            return
+        ptr = exchange_lists.wait(stream=main_stream)
+        blk = (1 + CAP) * 16
+        peers = yp.device_view(ptr, (n_gpus - 1) * blk).reshape(n_gpus - 1, 1 + CAP, 16)
+        for r in range(n_gpus):
+            gathered[r].copy_(list_buf if r == rank else peers[r if r < rank else r - 1])
+        torch.cuda.synchronize()
+
+    def exchange_find_all(mt):
+        """The timed step's sequence (push needles, own match, wait, split match, push list block) against matcher `mt`;
+        returns the merged match list, sorted by (row, needle).  COLLECTIVE; used by the parity leg."""
+        match_cnt.zero_()
+        exchange.post(local_needles, stream=main_stream)
+        mt.find_device(local_needles, q_loc, match_out, CAP, match_cnt, needle_base=rank * q_loc)
+        ptr = exchange.wait(stream=main_stream)
+        mt.find_device(ptr, q_all - q_loc, match_out, CAP, match_cnt, split_at=rank * q_loc, gap=q_loc)
+        exchange_lists.post(list_buf, stream=main_stream)
+        collect_lists()
+        g = gathered.cpu().numpy()
+        parts = []
+        for r in range(n_gpus):
+            n = int(g[r, 0, :4].view(np.int32)[0])
+            if n > CAP:
+                raise SystemExit(f"bench.py: parity: rank {r} reports {n} matches, list capacity {CAP}")
+            parts.append(g[r, 1:1 + n].reshape(-1).view(yp.MATCH_DTYPE).reshape(-1))
+        m = np.concatenate(parts)
+        dist.barrier()
+        return m[np.lexsort((m["needle"], m["row"]))]
 
     for _ in range(args.warmup):
         step()
@@ -440,8 +483,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step()
-    if n_gpus > 1:
-        main_stream.wait_event(ev_list)      # the last step's match lists have arrived on every rank
+    finish_lists()      # the last step's match lists have arrived on every rank
     e1.record()
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
@@ -464,10 +506,18 @@ def main():
         names = ["hashed", "gathered", "packed", "own_matched", "others_matched", "lists_gathered"]
         mine = {n: float(np.median([tl["start"].elapsed_time(tl[n]) for tl in tls[1:]])) for n in names}
         mine["next_start"] = float(np.median([tls[i]["start"].elapsed_time(tls[i + 1]["start"]) for i in range(1, 4)]))
+        per_rank = [None] * n_gpus
+        dist.all_gather_object(per_rank, {"own_match": mine["own_matched"] - mine["packed"],
+                                          "others_match": mine["others_matched"] - mine["own_matched"],
+                                          "step": mine["next_start"]})
         timeline = {"rank0_ms": mine, "max_over_ranks_ms": {n: max_over_ranks(v) for n, v in mine.items()},
-                    "note": "main stream: hashed -> own_matched -> others_matched; side stream: gathered (NCCL all-gather of "
-                            "the needles) -> packed (two D2D copies) and lists_gathered (NCCL all-gather of count + list, "
-                            "under the next step's hash)"}
+                    "per_rank_ms": per_rank,
+                    "note": ("one stream: hashed -> gathered = packed (needles pushed to every peer) -> own_matched -> [wait for "
+                             "the peers' needles] others_matched -> lists_gathered (list block pushed to every peer)")
+                    if exchange is not None else
+                    ("main stream: hashed -> own_matched -> others_matched; side stream: gathered (NCCL all-gather of "
+                     "the needles) -> packed (two D2D copies) and lists_gathered (NCCL all-gather of count + list, "
+                     "under the next step's hash)")}
         barrier()
 
     # ---- correctness of what was timed (untimed check) -----------------------
@@ -481,13 +531,15 @@ def main():
         raise SystemExit(f"bench.py: rank {rank}: {len(missing)} planted matches were not found")
     total_matches = n_matches
     if n_gpus > 1:
+        collect_lists()
         g = gathered.cpu().numpy()
         total_matches = int(sum(int(g[r, 0, :4].view(np.int32)[0]) for r in range(n_gpus)))
 
     # ---- parity: merged multi-GPU match list == CPU oracle on a sub-sampled problem ------
     parity = None
     if not args.no_parity:
-        parity = parity_leg(args, yp, sharded, dist, torch, dev, rank, n_gpus, local_rank, local_needles, needles_all, q_all)
+        parity = parity_leg(args, yp, sharded, dist, torch, dev, rank, n_gpus, local_rank, local_needles, needles_all, q_all,
+                            exchange_find_all if exchange is not None else None)
 
     # ---- per-kernel timings for the rooflines (CUDA events on the launch stream) ------
     def time_kernel(fn, iters, flush=None):
@@ -828,7 +880,8 @@ def main():
             "config5": c5, "config4": c4, "worst_case": worst, "step_timeline": timeline,
             "needle_gather": None if n_gpus == 1 else
             ("NCCL all-gather + two packing copies" if exchange is None else
-             "copy-engine pushes over peer memory (yume_pdq_cuda_exchange_*: CUDA IPC buffers, flag words, no kernel)"),
+             "one push kernel over peer memory before the matcher (yume_pdq_cuda_exchange_*: CUDA IPC buffers, NVLink stores, "
+             "flag words)"),
             "cpu_baseline": cpu_bl,
         }
         line.update(line_extra)
@@ -961,7 +1014,8 @@ PARITY_ROWS = 200_000
 PARITY_SCALAR_ROWS = 16_384      # rows (every stride-th of the 200,000) the scalar oracle checks, divided by N
 
 
-def parity_leg(args, yp, sharded, dist, torch, dev, rank, n_gpus, local_rank, local_needles, needles_all, q_all):
+def parity_leg(args, yp, sharded, dist, torch, dev, rank, n_gpus, local_rank, local_needles, needles_all, q_all,
+               exchange_find_all=None):
     """Full equality of the sharded matcher's merged match list with the CPU oracle, on a sub-sampled problem: a
     200,000-row synthetic DB (row-range sharded over the N ranks exactly like the timed one) x ALL q_all needles of
     the job.  Rank 0 compares (row, needle, distance) lists: against the AVX-512 port of the reference matcher on all
@@ -988,8 +1042,16 @@ def parity_leg(args, yp, sharded, dist, torch, dev, rank, n_gpus, local_rank, lo
     t0 = time.perf_counter()
     got = smp.find_all(local_needles, cap=1 << 14)        # all-gather needles -> shard scans -> gather + merge
     t_gpu = time.perf_counter() - t0
+    # the timed step's own data path (peer exchange + split match) on the same problem must give the same list
+    got_x = exchange_find_all(smp.matcher) if exchange_find_all is not None else None
     smp.close()
-    out = {"checked": False, "rows": PARITY_ROWS, "needles": int(q_all), "threshold": THRESHOLD,
+    if got_x is not None:
+        kx = [(int(r), int(n), int(d)) for r, n, d in zip(got_x["row"], got_x["needle"], got_x["dist"])]
+        kg = [(int(r), int(n), int(d)) for r, n, d in zip(got["row"], got["needle"], got["dist"])]
+        if kx != kg:
+            raise SystemExit(f"bench.py: PARITY FAILURE: rank {rank}: peer-exchange path ({len(kx)} matches) != "
+                             f"ShardedMatcher.find_all ({len(kg)} matches)")
+    out = {"checked": False, "exchange_path_checked": got_x is not None, "rows": PARITY_ROWS, "needles": int(q_all), "threshold": THRESHOLD,
            "matches": int(len(got)), "planted": len(planted), "sharded_find_all_ms": t_gpu * 1e3}
     if rank != 0:
         return out

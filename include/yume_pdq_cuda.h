@@ -210,13 +210,15 @@ int yume_pdq_cuda_mailbox_set_mode(YumePDQ_CudaMailbox *mb, int mode);
  * launches; answer in) */
 int yume_pdq_cuda_mailbox_last_timing(const YumePDQ_CudaMailbox *mb, double *out5);
 
-/* ---- needle all-gather over peer memory with the copy engines (one process per GPU, no kernel on the data path) ----
- * Every rank pushes its slice (slice_bytes, the same on every rank) into a buffer in every peer's HBM (CUDA IPC, copy-engine
- * copies over NVLink) followed, in stream order, by a sequence number in the peer's flag word; `wait` makes a stream wait
- * (one-warp kernel) until every peer's slice of the latest `post` is in and returns this rank's buffer: the world - 1
- * slices of the OTHER ranks in rank order -- the packed batch yume_pdq_cuda_matcher_find_device_split takes with
- * split_at = rank * needles_per_slice and gap = needles_per_slice.  Unlike an NCCL all-gather it needs no SM, so it does
- * not delay a persistent matcher kernel running beside it.
+/* ---- needle all-gather over peer memory (one process per GPU, no collective library on the data path) ----
+ * Every rank pushes its slice (slice_bytes, the same on every rank) into a buffer in every peer's HBM (CUDA IPC) followed by
+ * a sequence number in the peer's flag word; `wait` makes a stream wait (one-warp kernel) until every peer's slice of the
+ * latest `post` is in and returns this rank's buffer: the world - 1 slices of the OTHER ranks in rank order -- the packed
+ * batch yume_pdq_cuda_matcher_find_device_split takes with split_at = rank * needles_per_slice and gap =
+ * needles_per_slice.  How the slice travels: EXCHANGE_KERNEL -- one kernel stores it to all peers over NVLink and its last
+ * CTA releases the flags (~15-20 us for 1 MiB to 7 peers; issue it BEFORE a persistent matcher kernel, not beside it);
+ * EXCHANGE_COPY_ENGINE -- world - 1 peer copies + world - 1 four-byte flag copies in stream order (no launch of ours, but
+ * ~15 us per copy, and issued beside a persistent kernel the copies delay it as an NCCL all-gather does).
  *   create / connect : as for the mailboxes (handle_out: YUME_PDQ_CUDA_IPC_HANDLE_BYTES; handles rank-ordered)
  *   post   : COLLECTIVE, enqueues on `stream`; slice_dev must stay unchanged until the stream has passed this point
  *   wait   : enqueues on `stream`; *others_dev is valid until the post after next (two buffers alternate).  The caller
@@ -226,7 +228,9 @@ typedef struct YumePDQ_CudaExchange YumePDQ_CudaExchange;
 int yume_pdq_cuda_exchange_create(int device, int rank, int world, size_t slice_bytes, YumePDQ_CudaExchange **out,
                                   uint8_t *handle_out);
 int yume_pdq_cuda_exchange_connect(YumePDQ_CudaExchange *ex, const uint8_t *handles);
-int yume_pdq_cuda_exchange_post(YumePDQ_CudaExchange *ex, const void *slice_dev, void *stream);
+#define YUME_PDQ_CUDA_EXCHANGE_KERNEL 0
+#define YUME_PDQ_CUDA_EXCHANGE_COPY_ENGINE 1
+int yume_pdq_cuda_exchange_post(YumePDQ_CudaExchange *ex, const void *slice_dev, int how, void *stream);
 int yume_pdq_cuda_exchange_wait(YumePDQ_CudaExchange *ex, void *stream, const uint8_t **others_dev);
 int yume_pdq_cuda_exchange_failed(YumePDQ_CudaExchange *ex, int *failed);
 int yume_pdq_cuda_exchange_destroy(YumePDQ_CudaExchange *ex);

@@ -246,7 +246,7 @@ def _exchange_worker(rank, world, port, result_dir):
         done.record(main)
         with torch.cuda.stream(side):
             side.wait_event(done)
-            ex.post(mine, stream=side)
+            ex.post(mine, stream=side, how=yp.EXCHANGE_KERNEL if step % 3 else yp.EXCHANGE_COPY_ENGINE)
             ev.record(side)
         cnt.zero_()
         m.find_device(mine, q_loc, out, 1 << 12, cnt, needle_base=rank * q_loc)

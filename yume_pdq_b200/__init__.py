@@ -31,6 +31,7 @@ MATCH_DTYPE = np.dtype([("row", "<u8"), ("needle", "<u4"), ("dist", "<u4")])
 ALGO_AUTO, ALGO_EXACT, ALGO_TILED, ALGO_TENSOR, ALGO_TENSOR_I8 = 0, 1, 2, 4, 5
 ALGO_TENSOR_FULL, ALGO_TENSOR_PREFIX, ALGO_TENSOR_PAIRED, ALGO_TENSOR_ROWS = 6, 7, 8, 9
 MAILBOX_AUTO, MAILBOX_SEPARATE, MAILBOX_FUSED = 0, 1, 2
+EXCHANGE_KERNEL, EXCHANGE_COPY_ENGINE = 0, 1
 
 OP_T = 0
 OP_NEGATE_ALT_COLS_FALSE = 1
@@ -106,7 +107,7 @@ SIGNATURES = {
     "yume_pdq_cuda_mailbox_set_mode": (C.c_int, [_vp, C.c_int]),
     "yume_pdq_cuda_exchange_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(_vp), _vp]),
     "yume_pdq_cuda_exchange_connect": (C.c_int, [_vp, C.c_char_p]),
-    "yume_pdq_cuda_exchange_post": (C.c_int, [_vp, _vp, _vp]),
+    "yume_pdq_cuda_exchange_post": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "yume_pdq_cuda_exchange_wait": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "yume_pdq_cuda_exchange_failed": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "yume_pdq_cuda_exchange_destroy": (C.c_int, [_vp]),
@@ -651,6 +652,19 @@ class PeerMailbox:
             pass
 
 
+class _DeviceBytes:
+    """__cuda_array_interface__ over raw device memory (uint8)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": (int(nbytes),), "typestr": "|u1", "version": 2}
+
+
+def device_view(ptr: int, nbytes: int, device: int | None = None):
+    """A torch uint8 tensor over `nbytes` of device memory at `ptr` (no copy; the memory must outlive the tensor)."""
+    import torch
+    return torch.as_tensor(_DeviceBytes(ptr, nbytes), device=torch.device("cuda", torch.cuda.current_device() if device is None else device))
+
+
 class PeerExchange:
     """This rank's end of the copy-engine needle all-gather (yume_pdq_cuda_exchange_*): `handle` goes to the peers,
     `connect` takes everyone's handles in rank order; `post(slice)` pushes this rank's slice to every peer, `wait()`
@@ -669,8 +683,8 @@ class PeerExchange:
         assert len(blob) == self.world * IPC_HANDLE_BYTES
         _check(lib.yume_pdq_cuda_exchange_connect(self._h, C.c_char_p(blob)), "exchange_connect")
 
-    def post(self, slice_dev, stream=None):
-        _check(lib.yume_pdq_cuda_exchange_post(self._h, _ptr(slice_dev), _stream(stream)), "exchange_post")
+    def post(self, slice_dev, stream=None, how: int = EXCHANGE_KERNEL):
+        _check(lib.yume_pdq_cuda_exchange_post(self._h, _ptr(slice_dev), how, _stream(stream)), "exchange_post")
 
     def wait(self, stream=None) -> int:
         p = _vp()

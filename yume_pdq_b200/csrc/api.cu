@@ -1615,6 +1615,38 @@ __global__ void exchange_ring_kernel(unsigned int *ring)
         ring[i] = i;
 }
 
+struct ExchangePeers {
+    uint4 *dst[kMailboxMaxWorld];            // where this rank's slice goes in every peer's buffer (nullptr: this rank)
+    unsigned int *flag[kMailboxMaxWorld];    // the peer's flag word for this rank
+};
+
+// The push as ONE kernel: every 16-byte vector of the slice is loaded once and stored to all peers over NVLink; the last
+// CTA to finish (device-scope counter, system-scope fences) releases the sequence number into every peer's flag word.
+// Issued on the main stream BEFORE the persistent matcher it costs ~15-20 us and then shares the SMs with nobody.
+__global__ void __launch_bounds__(256)
+exchange_push_kernel(const uint4 *__restrict__ src, size_t n_vec, ExchangePeers peers, int world, unsigned int *done, uint32_t seq)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(src + i);
+        for (int p = 0; p < world; p++)
+            if (peers.dst[p])
+                peers.dst[p][i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ unsigned int last;
+    if (threadIdx.x == 0)
+        last = atomicAdd(done, 1u) == gridDim.x - 1u;
+    __syncthreads();
+    if (!last)
+        return;
+    if (threadIdx.x == 0)
+        *done = 0;
+    __threadfence_system();
+    if ((int)threadIdx.x < world && peers.flag[threadIdx.x])
+        st_release_sys(peers.flag[threadIdx.x], seq);
+}
+
 __global__ void __launch_bounds__(32)
 exchange_wait_kernel(ExchangeFlags *flags, int world, int rank, uint32_t want)
 {
@@ -1640,7 +1672,8 @@ struct YumePDQ_CudaExchange {
     uint32_t seq = 0;
     uint8_t *mine = nullptr;                    // [buf 0][buf 1][ExchangeFlags]
     uint8_t *peer[ypdq::kMailboxMaxWorld] = {nullptr};
-    unsigned int *ring = nullptr;               // local
+    unsigned int *ring = nullptr;               // local: [kExchangeRing sequence numbers][finished-CTA counter]
+    int sm_count = 148;
     bool connected = false;
     ypdq::ExchangeFlags *flags_of(uint8_t *base) const { return reinterpret_cast<ypdq::ExchangeFlags *>(base + 2 * buf_bytes); }
 };
@@ -1670,7 +1703,11 @@ int yume_pdq_cuda_exchange_create(int device, int rank, int world, size_t slice_
     if (e == cudaSuccess)
         e = cudaMemset(ex->mine + 2 * ex->buf_bytes, 0, sizeof(ExchangeFlags));
     if (e == cudaSuccess)
-        e = cudaMalloc(&ex->ring, kExchangeRing * sizeof(unsigned int));
+        e = cudaMalloc(&ex->ring, (kExchangeRing + 64) * sizeof(unsigned int));
+    if (e == cudaSuccess)
+        e = cudaMemset(ex->ring + kExchangeRing, 0, 64 * sizeof(unsigned int));
+    if (e == cudaSuccess)
+        e = cudaDeviceGetAttribute(&ex->sm_count, cudaDevAttrMultiProcessorCount, device);
     cudaIpcMemHandle_t h;
     if (e == cudaSuccess) {
         exchange_ring_kernel<<<kExchangeRing / 256, 256>>>(ex->ring);
@@ -1709,10 +1746,10 @@ int yume_pdq_cuda_exchange_connect(YumePDQ_CudaExchange *ex, const uint8_t *hand
     return 0;
 }
 
-int yume_pdq_cuda_exchange_post(YumePDQ_CudaExchange *ex, const void *slice_dev, void *stream)
+int yume_pdq_cuda_exchange_post(YumePDQ_CudaExchange *ex, const void *slice_dev, int how, void *stream)
 {
     using namespace ypdq;
-    if (!ex || !ex->connected || !slice_dev)
+    if (!ex || !ex->connected || !slice_dev || (how != YUME_PDQ_CUDA_EXCHANGE_KERNEL && how != YUME_PDQ_CUDA_EXCHANGE_COPY_ENGINE))
         return YUME_PDQ_CUDA_E_INVALID;
     int rc = ensure_device(ex->device);
     if (rc)
@@ -1720,6 +1757,24 @@ int yume_pdq_cuda_exchange_post(YumePDQ_CudaExchange *ex, const void *slice_dev,
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t seq = ++ex->seq;
     const size_t buf = (seq & 1u) * ex->buf_bytes;
+    if (how == YUME_PDQ_CUDA_EXCHANGE_KERNEL) {
+        if (ex->world == 1)
+            return 0;
+        ExchangePeers peers{};
+        for (int p = 0; p < ex->world; p++) {
+            if (p == ex->rank)
+                continue;
+            const size_t slot = (size_t)(ex->rank < p ? ex->rank : ex->rank - 1);
+            peers.dst[p] = reinterpret_cast<uint4 *>(ex->peer[p] + buf + slot * ex->slice_bytes);
+            peers.flag[p] = &ex->flags_of(ex->peer[p])->from[ex->rank];
+        }
+        const size_t n_vec = ex->slice_bytes / 16;
+        const unsigned grid = (unsigned)std::min<size_t>((n_vec + 255) / 256, (size_t)ex->sm_count * 4);
+        exchange_push_kernel<<<grid, 256, 0, s>>>(static_cast<const uint4 *>(slice_dev), n_vec, peers, ex->world,
+                                                  ex->ring + kExchangeRing, seq & (kExchangeRing - 1));
+        YPDQ_LAUNCH_CHECK();
+        return 0;
+    }
     // rank r's slice is slot (r < p ? r : r - 1) of peer p's buffer: p's buffer holds every slice but p's own, in rank order
     for (int d = 1; d < ex->world; d++) {
         const int p = (ex->rank + d) % ex->world;      // start with the next rank: the pushes of all ranks fan out evenly
