@@ -11,6 +11,8 @@ for what in "$@"; do
     tensor32k) K=match_tensor4x2 ;;
     tensor128) K=match_tensor4x2 ;;
     rows8) K=match_rows_m ;;
+    one) K=hash_one_kernel ;;
+    mailbox1) K=match_rows_m ;;
     *)      K=$what ;;
   esac
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 2 -c 1 -f -o $OUT/ncu_$what \

@@ -51,3 +51,20 @@ if {"scan", "stream", "tiled", "exact", "tensor", "tensor128", "tensor32k", "row
             m.find_device(nbig[:128].contiguous(), 128, out, 1 << 16, cnt, algo=yp.ALGO_TENSOR_PAIRED)
     torch.cuda.synchronize()
 print("done")
+
+if "one" in what:        # single-frame latency kernel (hash_one_kernel), frame already in device memory
+    f = torch.empty((1, 512, 512), dtype=torch.float32, device=dev)
+    yp.synth_frames(f, 1, kind=1)
+    torch.cuda.synchronize()
+    for _ in range(4):
+        yp.hash_get_threshold(f[0])
+if "mailbox1" in what:   # the peer-memory query folded into the rows-in-M scan, a world of one rank
+    n = (10_000_000 // 2048 + 1) * 2048
+    dbm = yp.CudaVectorDatabase(synthetic_rows=n)
+    mb = yp.PeerMailbox(0, 0, 1)
+    mb.connect([mb.handle])
+    q8 = rng.integers(0, 256, size=(8, 32), dtype=np.uint8)
+    for _ in range(4):
+        mb.scan(dbm, q8, 8, 31, root=0)
+    mb.close()
+    dbm.close()
