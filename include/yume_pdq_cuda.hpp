@@ -174,6 +174,15 @@ public:
             return out;
         }
     }
+    // asynchronous device-side scan (device pointers; count_dev is not reset); needle j is reported as needle_base + j,
+    // from split_at on as needle_base + gap + j (a batch that is a longer list with a hole cut out)
+    void find_device(const uint8_t *needles_dev, size_t q, YumePDQ_Match *out_dev, uint32_t cap, uint32_t *count_dev,
+                     uint32_t needle_base = 0, uint32_t split_at = 0xFFFFFFFFu, uint32_t gap = 0,
+                     int algo = YUME_PDQ_CUDA_ALGO_AUTO) const
+    {
+        check(yume_pdq_cuda_matcher_find_device_split(db_, needles_dev, q, threshold_, out_dev, cap, count_dev, algo, needle_base,
+                                                      split_at, gap, stream_), "find_device");
+    }
     // PDQMatcher::find: f(hay_idx, needle_idx) -> std::optional<R>; first engaged value wins
     template <class R, class F>
     std::optional<R> find(const uint8_t *needles, size_t q, F &&f) const
@@ -187,6 +196,51 @@ private:
     YumePDQ_CudaDb *db_;
     uint32_t threshold_;
     void *stream_;
+};
+
+// ---- one process per GPU: peer-memory mailboxes (the sharded VulkanMatcher::scan) and the needle exchange ----
+// `handle()` goes to the peers (any transport), `connect` takes everyone's handles in rank order.
+class PeerMailbox {
+public:
+    PeerMailbox(int device, int rank, int world) { check(yume_pdq_cuda_mailbox_create(device, rank, world, &mb_, handle_), "mailbox_create"); }
+    PeerMailbox(const PeerMailbox &) = delete;
+    ~PeerMailbox() { yume_pdq_cuda_mailbox_destroy(mb_); }
+    const uint8_t *handle() const { return handle_; }
+    void connect(const uint8_t *handles) { check(yume_pdq_cuda_mailbox_connect(mb_, handles), "mailbox_connect"); }
+    void set_mode(int mode) { check(yume_pdq_cuda_mailbox_set_mode(mb_, mode), "mailbox_set_mode"); }
+    // COLLECTIVE; on the root: bit r set = rank r's shard holds a match
+    uint32_t scan(const CudaVectorDatabase &shard, const uint8_t *needles, size_t q, uint32_t threshold, int root, void *stream = nullptr)
+    {
+        uint32_t mask = 0;
+        check(yume_pdq_cuda_mailbox_scan(mb_, shard.raw(), needles, q, threshold, root, &mask, stream), "mailbox_scan");
+        return mask;
+    }
+private:
+    YumePDQ_CudaMailbox *mb_ = nullptr;
+    uint8_t handle_[YUME_PDQ_CUDA_IPC_HANDLE_BYTES];
+};
+
+class PeerExchange {
+public:
+    PeerExchange(int device, int rank, int world, size_t slice_bytes)
+    { check(yume_pdq_cuda_exchange_create(device, rank, world, slice_bytes, &ex_, handle_), "exchange_create"); }
+    PeerExchange(const PeerExchange &) = delete;
+    ~PeerExchange() { yume_pdq_cuda_exchange_destroy(ex_); }
+    const uint8_t *handle() const { return handle_; }
+    void connect(const uint8_t *handles) { check(yume_pdq_cuda_exchange_connect(ex_, handles), "exchange_connect"); }
+    void post(const void *slice_dev, void *stream = nullptr, int how = YUME_PDQ_CUDA_EXCHANGE_KERNEL)
+    { check(yume_pdq_cuda_exchange_post(ex_, slice_dev, how, stream), "exchange_post"); }
+    // the other ranks' slices of the latest post, packed in rank order (valid until the post after next)
+    const uint8_t *wait(void *stream = nullptr)
+    {
+        const uint8_t *p = nullptr;
+        check(yume_pdq_cuda_exchange_wait(ex_, stream, &p), "exchange_wait");
+        return p;
+    }
+    bool failed() { int f = 0; check(yume_pdq_cuda_exchange_failed(ex_, &f), "exchange_failed"); return f != 0; }
+private:
+    YumePDQ_CudaExchange *ex_ = nullptr;
+    uint8_t handle_[YUME_PDQ_CUDA_IPC_HANDLE_BYTES];
 };
 
 }  // namespace ypdq

@@ -6,6 +6,12 @@ use core::ffi::{c_char, c_int, c_void};
 pub struct YumePDQ_CudaDb { _private: [u8; 0] }
 
 #[repr(C)]
+pub struct YumePDQ_CudaMailbox { _private: [u8; 0] }
+#[repr(C)]
+pub struct YumePDQ_CudaExchange { _private: [u8; 0] }
+pub const IPC_HANDLE_BYTES: usize = 64;
+
+#[repr(C)]
 #[derive(Debug, Clone, Copy, PartialEq, Eq, Default)]
 pub struct YumePDQ_Match { pub row: u64, pub needle: u32, pub dist: u32 }
 
@@ -50,4 +56,24 @@ unsafe extern "C" {
     pub fn yume_pdq_cuda_screen_batch_pixels(db: *mut YumePDQ_CudaDb, frames: *const c_void, pixel_format: c_int,
         n: usize, threshold: u32, hashes: *mut u8, quality: *mut f32, out: *mut YumePDQ_Match, cap: usize,
         n_found: *mut usize, stream: *mut c_void) -> c_int;
+    // ---- one process per GPU (sharded database): device-side scans, peer-memory mailboxes, needle exchange ----
+    pub fn yume_pdq_cuda_matcher_find_device_split(db: *mut YumePDQ_CudaDb, needles_dev: *const u8, q: usize,
+        threshold: u32, out_dev: *mut YumePDQ_Match, cap: u32, count_dev: *mut u32, algo: c_int, needle_base: u32,
+        split_at: u32, gap: u32, stream: *mut c_void) -> c_int;
+    pub fn yume_pdq_cuda_mailbox_create(device: c_int, rank: c_int, world: c_int, out: *mut *mut YumePDQ_CudaMailbox,
+        handle_out: *mut u8) -> c_int;
+    pub fn yume_pdq_cuda_mailbox_connect(mb: *mut YumePDQ_CudaMailbox, handles: *const u8) -> c_int;
+    pub fn yume_pdq_cuda_mailbox_set_mode(mb: *mut YumePDQ_CudaMailbox, mode: c_int) -> c_int;
+    pub fn yume_pdq_cuda_mailbox_scan(mb: *mut YumePDQ_CudaMailbox, db: *mut YumePDQ_CudaDb, needles: *const u8, q: usize,
+        threshold: u32, root: c_int, matched_ranks: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn yume_pdq_cuda_mailbox_destroy(mb: *mut YumePDQ_CudaMailbox) -> c_int;
+    pub fn yume_pdq_cuda_exchange_create(device: c_int, rank: c_int, world: c_int, slice_bytes: usize,
+        out: *mut *mut YumePDQ_CudaExchange, handle_out: *mut u8) -> c_int;
+    pub fn yume_pdq_cuda_exchange_connect(ex: *mut YumePDQ_CudaExchange, handles: *const u8) -> c_int;
+    pub fn yume_pdq_cuda_exchange_post(ex: *mut YumePDQ_CudaExchange, slice_dev: *const c_void, how: c_int,
+        stream: *mut c_void) -> c_int;
+    pub fn yume_pdq_cuda_exchange_wait(ex: *mut YumePDQ_CudaExchange, stream: *mut c_void,
+        others_dev: *mut *const u8) -> c_int;
+    pub fn yume_pdq_cuda_exchange_failed(ex: *mut YumePDQ_CudaExchange, failed: *mut c_int) -> c_int;
+    pub fn yume_pdq_cuda_exchange_destroy(ex: *mut YumePDQ_CudaExchange) -> c_int;
 }
