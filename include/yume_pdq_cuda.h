@@ -231,6 +231,9 @@ int yume_pdq_cuda_exchange_connect(YumePDQ_CudaExchange *ex, const uint8_t *hand
 #define YUME_PDQ_CUDA_EXCHANGE_KERNEL 0
 #define YUME_PDQ_CUDA_EXCHANGE_COPY_ENGINE 1
 int yume_pdq_cuda_exchange_post(YumePDQ_CudaExchange *ex, const void *slice_dev, int how, void *stream);
+/* a shorter slice this time (bytes <= slice_bytes, a multiple of 16, the same on every rank): the peers' buffers then hold
+ * world - 1 slices of `bytes`, packed -- the last, partial chunk of a chunked pipeline */
+int yume_pdq_cuda_exchange_post_bytes(YumePDQ_CudaExchange *ex, const void *slice_dev, size_t bytes, int how, void *stream);
 int yume_pdq_cuda_exchange_wait(YumePDQ_CudaExchange *ex, void *stream, const uint8_t **others_dev);
 int yume_pdq_cuda_exchange_failed(YumePDQ_CudaExchange *ex, int *failed);
 int yume_pdq_cuda_exchange_destroy(YumePDQ_CudaExchange *ex);

@@ -108,6 +108,7 @@ SIGNATURES = {
     "yume_pdq_cuda_exchange_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(_vp), _vp]),
     "yume_pdq_cuda_exchange_connect": (C.c_int, [_vp, C.c_char_p]),
     "yume_pdq_cuda_exchange_post": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "yume_pdq_cuda_exchange_post_bytes": (C.c_int, [_vp, _vp, C.c_size_t, C.c_int, _vp]),
     "yume_pdq_cuda_exchange_wait": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "yume_pdq_cuda_exchange_failed": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "yume_pdq_cuda_exchange_destroy": (C.c_int, [_vp]),
@@ -683,8 +684,10 @@ class PeerExchange:
         assert len(blob) == self.world * IPC_HANDLE_BYTES
         _check(lib.yume_pdq_cuda_exchange_connect(self._h, C.c_char_p(blob)), "exchange_connect")
 
-    def post(self, slice_dev, stream=None, how: int = EXCHANGE_KERNEL):
-        _check(lib.yume_pdq_cuda_exchange_post(self._h, _ptr(slice_dev), how, _stream(stream)), "exchange_post")
+    def post(self, slice_dev, stream=None, how: int = EXCHANGE_KERNEL, nbytes: int | None = None):
+        """``nbytes``: a shorter slice this time (the same on every rank); the peers' buffers are packed at that stride."""
+        _check(lib.yume_pdq_cuda_exchange_post_bytes(self._h, _ptr(slice_dev), self.slice_bytes if nbytes is None else nbytes,
+                                                     how, _stream(stream)), "exchange_post")
 
     def wait(self, stream=None) -> int:
         p = _vp()

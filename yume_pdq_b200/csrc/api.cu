@@ -1748,8 +1748,14 @@ int yume_pdq_cuda_exchange_connect(YumePDQ_CudaExchange *ex, const uint8_t *hand
 
 int yume_pdq_cuda_exchange_post(YumePDQ_CudaExchange *ex, const void *slice_dev, int how, void *stream)
 {
+    return ex ? yume_pdq_cuda_exchange_post_bytes(ex, slice_dev, ex->slice_bytes, how, stream) : YUME_PDQ_CUDA_E_INVALID;
+}
+
+int yume_pdq_cuda_exchange_post_bytes(YumePDQ_CudaExchange *ex, const void *slice_dev, size_t bytes, int how, void *stream)
+{
     using namespace ypdq;
-    if (!ex || !ex->connected || !slice_dev || (how != YUME_PDQ_CUDA_EXCHANGE_KERNEL && how != YUME_PDQ_CUDA_EXCHANGE_COPY_ENGINE))
+    if (!ex || !ex->connected || !slice_dev || (how != YUME_PDQ_CUDA_EXCHANGE_KERNEL && how != YUME_PDQ_CUDA_EXCHANGE_COPY_ENGINE) ||
+        bytes == 0 || bytes > ex->slice_bytes || bytes % 16 != 0)
         return YUME_PDQ_CUDA_E_INVALID;
     int rc = ensure_device(ex->device);
     if (rc)
@@ -1765,10 +1771,10 @@ int yume_pdq_cuda_exchange_post(YumePDQ_CudaExchange *ex, const void *slice_dev,
             if (p == ex->rank)
                 continue;
             const size_t slot = (size_t)(ex->rank < p ? ex->rank : ex->rank - 1);
-            peers.dst[p] = reinterpret_cast<uint4 *>(ex->peer[p] + buf + slot * ex->slice_bytes);
+            peers.dst[p] = reinterpret_cast<uint4 *>(ex->peer[p] + buf + slot * bytes);
             peers.flag[p] = &ex->flags_of(ex->peer[p])->from[ex->rank];
         }
-        const size_t n_vec = ex->slice_bytes / 16;
+        const size_t n_vec = bytes / 16;
         const unsigned grid = (unsigned)std::min<size_t>((n_vec + 255) / 256, (size_t)ex->sm_count * 4);
         exchange_push_kernel<<<grid, 256, 0, s>>>(static_cast<const uint4 *>(slice_dev), n_vec, peers, ex->world,
                                                   ex->ring + kExchangeRing, seq & (kExchangeRing - 1));
@@ -1779,7 +1785,7 @@ int yume_pdq_cuda_exchange_post(YumePDQ_CudaExchange *ex, const void *slice_dev,
     for (int d = 1; d < ex->world; d++) {
         const int p = (ex->rank + d) % ex->world;      // start with the next rank: the pushes of all ranks fan out evenly
         const size_t slot = (size_t)(ex->rank < p ? ex->rank : ex->rank - 1);
-        YPDQ_CUDA_TRY(cudaMemcpyAsync(ex->peer[p] + buf + slot * ex->slice_bytes, slice_dev, ex->slice_bytes, cudaMemcpyDeviceToDevice, s));
+        YPDQ_CUDA_TRY(cudaMemcpyAsync(ex->peer[p] + buf + slot * bytes, slice_dev, bytes, cudaMemcpyDeviceToDevice, s));
     }
     for (int d = 1; d < ex->world; d++) {
         const int p = (ex->rank + d) % ex->world;

@@ -119,6 +119,7 @@ class ShardedMatcher:
         self.db = rows_factory(self.begin, self.end, device)
         self.matcher = CudaMatcher(self.db, threshold)
         self._mailbox = None
+        self._exchange = None       # (chunk, PeerExchange): the needle exchange of screen()
 
     def find_all(self, local_needles, cap: int = 1 << 16) -> np.ndarray:
         """local_needles: this rank's [q_local, 32] uint8 CUDA tensor.  Returns the merged global match
@@ -137,8 +138,9 @@ class ShardedMatcher:
         ``local_frames``: this rank's [n_local, 512, 512] f32 frames (or 8-bit frames in ``pixel_format``:
         u8 [n, 512, 512], [n, 512, 512, 3] or [n, 512, 512, 4]) -- a (pinned) host numpy array / CPU tensor,
         or a CUDA tensor; every rank passes the same n_local.  Per chunk of ``chunk`` frames:
-        [H2D of chunk i+1 on a copy stream] || [hash chunk i -> all-gather its 8 * chunk needles over
-        NCCL -> match the world * 8 * chunk gathered needles against this rank's row shard].  One host
+        [H2D of chunk i+1 on a copy stream] || [hash chunk i -> push its 8 * chunk needles into every peer's HBM
+        (PeerExchange: one kernel over NVLink, no collective library) -> match this rank's own needles -> wait for the
+        peers' -> match them in one launch (find_device_split), all against this rank's row shard].  One host
         synchronisation at the end, then the gather + merge of the match lists.  Returns, on every rank,
         all matches sorted by (row, needle) with needle = 8 * global_frame + dihedral and
         global_frame = rank * n_local + local index.  ``hashes_out`` ([n_local, 8, 32] uint8 CUDA tensor)
@@ -159,7 +161,11 @@ class ShardedMatcher:
         # with the legacy default stream, so launching on stream 0 under torch.cuda.stream(...) would race)
         kern = CudaKernel(self.device, stream=main)
         hashes = hashes_out if hashes_out is not None else torch.empty((n, 8, 32), dtype=torch.uint8, device=dev)
-        gath = [torch.empty((W * chunk * 8, 32), dtype=torch.uint8, device=dev) for _ in range(2)]
+        if self._exchange is None or self._exchange[0] != chunk:
+            if self._exchange is not None:
+                self._exchange[1].close()
+            self._exchange = (chunk, make_exchange(self.device, self.rank, W, chunk * 8 * 32, group=self.group))
+        ex = self._exchange[1]
         out = torch.zeros((cap, 16), dtype=torch.uint8, device=dev)
         cnt = torch.zeros(1, dtype=torch.int32, device=dev)
         if on_host:
@@ -187,10 +193,16 @@ class ShardedMatcher:
                             pixel_format=pixel_format)
             if on_host:
                 ev_done[b].record(main)
-            g = gath[b][: W * k * 8]
-            dist.all_gather_into_tensor(g, hashes[f0:f0 + k].reshape(-1, 32), group=self.group)
-            # chunk-local needle index p = r * 8k + i; rebased below to 8 * (r * n + f0) + i
-            self.matcher.find_device(g, W * k * 8, out, cap, cnt, needle_base=c * W * chunk * 8, stream=main)
+            # chunk-local needle index p = r * 8k + i (rank r, needle i of its chunk); rebased below to 8 * (r * n + f0) + i.
+            # A rank can never be two exchanges ahead of a peer: its push of chunk c + 2 follows its wait for chunk c + 1,
+            # which needs the peer's push of c + 1, which follows the peer's last read of chunk c (stream order).
+            mine = hashes[f0:f0 + k].reshape(-1, 32)
+            ex.post(mine, stream=main, nbytes=k * 8 * 32)
+            base = c * W * chunk * 8
+            self.matcher.find_device(mine, k * 8, out, cap, cnt, needle_base=base + self.rank * k * 8, stream=main)
+            others = ex.wait(stream=main)
+            self.matcher.find_device(others, (W - 1) * k * 8, out, cap, cnt, needle_base=base, split_at=self.rank * k * 8,
+                                     gap=k * 8, stream=main)
         # every rank must take the same decision about a retry (the retry runs collectives): agree on the
         # largest per-rank match count
         worst = cnt.to(torch.int64)
@@ -240,4 +252,7 @@ class ShardedMatcher:
         if self._mailbox is not None:
             self._mailbox.close()
             self._mailbox = None
+        if self._exchange is not None:
+            self._exchange[1].close()
+            self._exchange = None
         self.db.close()
