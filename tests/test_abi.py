@@ -101,3 +101,26 @@ def test_rust_overlay_lists_every_cuda_source():
     r = subprocess.run(["bash", os.path.join(root, "integration", "rust", "check.sh")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "CUDA sources" in r.stdout
+
+
+def test_cpp_mirror_compiles_and_links(tmp_path):
+    """include/yume_pdq_cuda.hpp (CudaKernel, CudaVectorDatabase, CudaMatcher incl. find_device / split, PeerMailbox,
+    PeerExchange) instantiates against the library: every member a C++ user can call names an exported symbol."""
+    import subprocess
+    src = tmp_path / "mirror.cpp"
+    src.write_text(
+        '#include "yume_pdq_cuda.hpp"\n'
+        "int main(int argc, char **) {\n"
+        "    if (argc < 100) return 0;                 // link only: no device in the build container\n"
+        "    ypdq::CudaVectorDatabase db(0, nullptr, 0);\n"
+        "    ypdq::CudaMatcher m(db, 31);\n"
+        "    m.find_device(nullptr, 0, nullptr, 0, nullptr, 0, 5, 7);\n"
+        "    ypdq::PeerMailbox mb(0, 0, 1); mb.connect(mb.handle()); mb.set_mode(YUME_PDQ_CUDA_MAILBOX_FUSED);\n"
+        "    mb.scan(db, nullptr, 8, 31, 0);\n"
+        "    ypdq::PeerExchange ex(0, 0, 1, 1024); ex.connect(ex.handle()); ex.post(nullptr); ex.wait(); ex.failed();\n"
+        "    return (int)m.scan(nullptr, 0);\n"
+        "}\n")
+    lib_dir = os.path.join(ROOT, "yume_pdq_b200")
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), str(src), "-L" + lib_dir,
+                    "-lyume_pdq_cuda", "-Wl,-rpath," + lib_dir, "-o", str(tmp_path / "mirror")], check=True, timeout=300)
+    assert subprocess.run([str(tmp_path / "mirror")], timeout=60).returncode == 0
