@@ -50,3 +50,91 @@ def test_sources_still_say_so():
     assert re.search(r"ex->rank < p \? ex->rank : ex->rank - 1", api)
     common = open(os.path.join(ROOT, "yume_pdq_b200", "csrc", "common.cuh")).read()
     assert re.search(r"return base \+ j \+ \(j >= split_at \? gap : 0u\);", common)
+
+
+# ---- the "never two exchanges ahead" argument of yume_pdq_cuda.h / ShardedMatcher.screen, checked on a model ----------
+def _simulate(world: int, steps: int, seed: int):
+    """Every rank runs, in stream order:  post(c) -> own_match(c) -> wait(c) -> others_begin(c) .. others_end(c)  for
+    c = 1 .. steps, with two buffers alternating by c & 1 (csrc/api.cu).  A random scheduler interleaves the ranks; a push
+    is split into one event per peer (the kernel's stores reach the peers at different times) followed by the flag
+    stores.  Returns the number of pushes that landed in a buffer a peer was still reading (must be 0)."""
+    import random
+    rnd = random.Random(seed)
+    flags = [[0] * world for _ in range(world)]            # flags[p][r]: last sequence number rank r pushed to p
+    reading = [None] * world                               # parity of the buffer rank p is matching from, if any
+    violations = 0
+    progs = []
+    for r in range(world):
+        ops = []
+        for c in range(1, steps + 1):
+            peers = [p for p in range(world) if p != r]
+            rnd.shuffle(peers)
+            ops += [("data", c, p) for p in peers] + [("flag", c, p) for p in peers]
+            ops += [("own", c, None), ("wait", c, None), ("begin", c, None), ("end", c, None)]
+        progs.append(ops)
+    pc = [0] * world
+    while any(pc[r] < len(progs[r]) for r in range(world)):
+        runnable = []
+        for r in range(world):
+            if pc[r] == len(progs[r]):
+                continue
+            kind, c, p = progs[r][pc[r]]
+            if kind == "wait" and any(flags[r][q] < c for q in range(world) if q != r):
+                continue
+            runnable.append(r)
+        assert runnable, "deadlock"
+        r = rnd.choice(runnable)
+        kind, c, p = progs[r][pc[r]]
+        pc[r] += 1
+        if kind == "data":
+            if reading[p] == (c & 1):
+                violations += 1
+        elif kind == "flag":
+            flags[p][r] = c
+        elif kind == "begin":
+            reading[r] = c & 1
+        elif kind == "end":
+            reading[r] = None
+    return violations
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_two_buffers_suffice_without_a_per_step_collective(world):
+    for seed in range(40):
+        assert _simulate(world, 12, seed) == 0
+
+
+def test_model_detects_a_missing_wait():
+    """sanity of the model itself: with ONE buffer (parity always 0) a fast rank does overwrite a slow reader"""
+    import random
+
+    def one_buffer(world, steps, seed):
+        rnd = random.Random(seed)
+        flags = [[0] * world for _ in range(world)]
+        reading = [False] * world
+        bad = 0
+        progs = []
+        for r in range(world):
+            ops = []
+            for c in range(1, steps + 1):
+                peers = [p for p in range(world) if p != r]
+                ops += [("data", c, p) for p in peers] + [("flag", c, p) for p in peers] + [("wait", c, None), ("begin", c, None), ("end", c, None)]
+            progs.append(ops)
+        pc = [0] * world
+        while any(pc[r] < len(progs[r]) for r in range(world)):
+            runnable = [r for r in range(world) if pc[r] < len(progs[r]) and not (
+                progs[r][pc[r]][0] == "wait" and any(flags[r][q] < progs[r][pc[r]][1] for q in range(world) if q != r))]
+            r = rnd.choice(runnable)
+            kind, c, p = progs[r][pc[r]]
+            pc[r] += 1
+            if kind == "data" and reading[p]:
+                bad += 1
+            elif kind == "flag":
+                flags[p][r] = c
+            elif kind == "begin":
+                reading[r] = True
+            elif kind == "end":
+                reading[r] = False
+        return bad
+
+    assert sum(one_buffer(3, 12, s) for s in range(40)) > 0
