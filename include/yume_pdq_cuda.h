@@ -189,7 +189,13 @@ int yume_pdq_cuda_one_frame_last_timing(double *out4, long long *kernel_clocks7)
  *             The root passes the needles (host or device pointer), the others NULL.  On the root *matched_ranks receives
  *             a bit mask (bit r: rank r's shard holds a row within the threshold of some needle) and the call returns when
  *             the answer is in; on the other ranks the call only enqueues on `stream` (their answer travels to the root
- *             on the device) and *matched_ranks is 0.  YUME_PDQ_CUDA_E_TIMEOUT if a peer did not take part within 2 s. */
+ *             on the device) and *matched_ranks is 0.  YUME_PDQ_CUDA_E_TIMEOUT if a peer did not take part within 2 s.
+ *             CHANGING THE ROOT: the root's call returns once every rank has answered, i.e. is done with its mailbox, and
+ *             only the root learns that.  A different rank may therefore become the root only after the previous root's
+ *             call has returned (any host-side ordering between the two processes, e.g. a barrier;
+ *             yume_pdq_b200.sharded.ShardedMatcher.scan_from inserts one when the root changes) -- otherwise its needles
+ *             could overwrite a mailbox that a slower rank, the previous root included, is still scanning from
+ *             (tests/test_exchange_layout.py models both cases). */
 #define YUME_PDQ_CUDA_IPC_HANDLE_BYTES 64
 typedef struct YumePDQ_CudaMailbox YumePDQ_CudaMailbox;
 int yume_pdq_cuda_mailbox_create(int device, int rank, int world, YumePDQ_CudaMailbox **out, uint8_t *handle_out);

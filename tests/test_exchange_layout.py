@@ -138,3 +138,83 @@ def test_model_detects_a_missing_wait():
         return bad
 
     assert sum(one_buffer(3, 12, s) for s in range(40)) > 0
+
+
+# ---- the mailbox query: why a CHANGE of root needs the previous root's call to have returned (yume_pdq_cuda.h) -------
+def _simulate_mailbox(world: int, roots, seed: int, barrier_on_root_change: bool) -> int:
+    """Hosts enqueue one kernel per query; a non-root's call returns at once, the root's when every rank has answered.
+    GPU streams run their kernels in order:  [root: needles -> every mailbox, then the flag]  wait for the flag  scan
+    (reads its own mailbox from begin to end)  answer -> root.  Returns how often needles were written into a mailbox
+    that its owner was still scanning from (or had not even read yet)."""
+    import random
+    rnd = random.Random(seed)
+    n_q = len(roots)
+    flag = [0] * world                      # seq_in of every mailbox
+    answers = [set() for _ in range(n_q + 1)]
+    scanning = [False] * world
+    host_pc = [1] * world                   # next query the host of rank r will enqueue
+    returned = [0] * world                  # last query whose call has returned on rank r
+    gpu = [[] for _ in range(world)]        # enqueued, not yet executed GPU events
+    bad = 0
+
+    def enqueue(r, seq):
+        root = roots[seq - 1]
+        ops = []
+        if r == root:
+            ops += [("data", seq, p) for p in range(world)] + [("flag", seq, p) for p in range(world)]
+        ops += [("wait", seq, None), ("begin", seq, None), ("end", seq, None), ("answer", seq, root)]
+        gpu[r] += ops
+
+    while any(returned[r] < n_q for r in range(world)):
+        moves = []
+        for r in range(world):
+            seq = host_pc[r]
+            if seq <= n_q and returned[r] == seq - 1:
+                changed = seq > 1 and roots[seq - 1] != roots[seq - 2]
+                if not (barrier_on_root_change and changed) or all(returned[x] >= seq - 1 for x in range(world)):
+                    moves.append(("enqueue", r))
+            if seq <= n_q + 1 and returned[r] < seq - 1:
+                # the call of query seq - 1 is still open: only the root's blocks
+                q = seq - 1
+                if roots[q - 1] != r or len(answers[q]) == world:
+                    moves.append(("return", r))
+            if gpu[r]:
+                kind, seq_g, p = gpu[r][0]
+                if not (kind == "wait" and flag[r] < seq_g):
+                    moves.append(("gpu", r))
+        if not moves:
+            return bad + 1000               # a flag went backwards (two roots' stores crossed): the real kernels time out
+        what, r = rnd.choice(moves)
+        if what == "enqueue":
+            enqueue(r, host_pc[r])
+            host_pc[r] += 1
+        elif what == "return":
+            returned[r] = host_pc[r] - 1
+        else:
+            kind, seq_g, p = gpu[r].pop(0)
+            if kind == "data" and scanning[p]:
+                bad += 1
+            elif kind == "wait" and flag[r] != seq_g:
+                bad += 1                    # the next query's needles are already here (the real kernel would time out)
+            elif kind == "flag":
+                flag[p] = seq_g
+            elif kind == "begin":
+                scanning[r] = True
+            elif kind == "end":
+                scanning[r] = False
+            elif kind == "answer":
+                answers[seq_g].add(r)
+    return bad
+
+
+def test_mailbox_root_change_needs_the_previous_call_to_have_returned():
+    same_root = [0] * 8
+    changing = [0, 1, 2, 0, 2, 1, 1, 0]
+    assert sum(_simulate_mailbox(3, same_root, s, False) for s in range(60)) == 0      # one root: nothing to add
+    # a new root posts as soon as ITS OWN previous kernel is done: the old root (or any third rank) may still be scanning
+    assert sum(_simulate_mailbox(2, [0, 1] * 4, s, False) for s in range(60)) > 0
+    assert sum(_simulate_mailbox(3, changing, s, False) for s in range(200)) > 0
+    # ShardedMatcher.scan_from's barrier when the root changes: the previous root's call has returned = everyone is done
+    assert sum(_simulate_mailbox(2, [0, 1] * 4, s, True) for s in range(60)) == 0
+    assert sum(_simulate_mailbox(3, changing, s, True) for s in range(200)) == 0
+    assert sum(_simulate_mailbox(8, [i % 8 for i in range(10)], s, True) for s in range(20)) == 0

@@ -119,6 +119,7 @@ class ShardedMatcher:
         self.db = rows_factory(self.begin, self.end, device)
         self.matcher = CudaMatcher(self.db, threshold)
         self._mailbox = None
+        self._last_root = None      # root of the previous scan_from query
         self._exchange = None       # (chunk, PeerExchange): the needle exchange of screen()
 
     def find_all(self, local_needles, cap: int = 1 << 16) -> np.ndarray:
@@ -246,6 +247,14 @@ class ShardedMatcher:
             mb.connect(handles)
             dist.barrier(group=self.group)
             self._mailbox = mb
+        if self._last_root is not None and root != self._last_root:
+            # A root returns only once every rank has answered, i.e. finished reading its mailbox -- but only the ROOT
+            # knows that.  A different rank may therefore post the next query's needles only after the previous root's
+            # call has returned: a slower rank (the previous root included) could otherwise still be scanning, and
+            # verifying candidates against, the mailbox the new root overwrites.  Same-root sequences need nothing.
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
+        self._last_root = root
         return self._mailbox.scan(self.db, needles if self.rank == root else None, q, self.matcher.threshold, root)
 
     def close(self):
