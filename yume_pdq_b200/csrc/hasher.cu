@@ -744,7 +744,8 @@ hash_one_kernel(const float *__restrict__ frame, float *buf1_dev, unsigned int *
         }
         buf1_dev[oi * 128 + tid] = sum;
         out->buf1[oi * 128 + tid] = sum;
-        __threadfence();
+        // system scope: this row of buf1 sits in HOST memory and must be there before the finishing CTA's sequence number
+        __threadfence_system();
     }
     __syncthreads();
     if (tid == 0)
